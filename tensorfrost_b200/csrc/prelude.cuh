@@ -1,0 +1,150 @@
+// Device prelude for kernels emitted by the CUDA code generator (tensorfrost_b200/overlay/.../CUDA.cpp).
+// It is the sm_100a restatement of the reference's C++ helper header
+// (TensorFrost/Backend/CodeGen/Langs/CPP.cpp:31-271): every helper an emitted kernel can call, with the
+// SAME arithmetic as the oracle so fp32 results agree to the last bit wherever libm/CUDA agree.
+// Compiled by NVRTC (no system headers), so only builtins are used.
+//
+// Naming: the emitter maps every IR function op `f` to `tf_f` (name_map_), so user variable names can
+// never shadow a helper.  Buffers are arrays of 32-bit words (`uint`), typed access is by bit
+// reinterpretation (Generators.cpp:399-437).
+
+typedef unsigned int uint;
+
+#ifndef TF_QUIRK_INT_AND_IS_OR
+// The oracle implements InterlockedAnd(int*) with fetch_or (CPP.cpp:183-187).  Parity with the
+// C++/OpenMP backend means reproducing it; build kernels with -DTF_QUIRK_INT_AND_IS_OR=0 for a true AND.
+#define TF_QUIRK_INT_AND_IS_OR 1
+#endif
+
+#define TF_DEV static __device__ __forceinline__
+
+// ---- bit casts (CPP.cpp:53-96) ------------------------------------------------------------
+TF_DEV float asfloat(uint x) { return __uint_as_float(x); }
+TF_DEV float asfloat(int x) { return __int_as_float(x); }
+TF_DEV float asfloat(float x) { return x; }
+TF_DEV uint asuint(float x) { return __float_as_uint(x); }
+TF_DEV uint asuint(int x) { return (uint)x; }
+TF_DEV uint asuint(uint x) { return x; }
+TF_DEV uint asuint(bool x) { return x ? 1u : 0u; }
+TF_DEV int asint(uint x) { return (int)x; }
+TF_DEV int asint(int x) { return x; }
+TF_DEV int asint(float x) { return __float_as_int(x); }
+TF_DEV int asint(bool x) { return x ? 1 : 0; }
+TF_DEV bool asbool(uint x) { return x != 0u; }
+TF_DEV bool asbool(int x) { return x != 0; }
+TF_DEV bool asbool(bool x) { return x; }
+TF_DEV bool asbool(float x) { return __float_as_uint(x) != 0u; }
+
+// ---- min / max / clamp: `a < b ? a : b`, NOT fminf (NaN behaviour follows the oracle, CPP.cpp:33-51,98-106)
+TF_DEV int tf_min(int a, int b) { return a < b ? a : b; }
+TF_DEV int tf_max(int a, int b) { return a > b ? a : b; }
+TF_DEV uint tf_min(uint a, uint b) { return a < b ? a : b; }
+TF_DEV uint tf_max(uint a, uint b) { return a > b ? a : b; }
+TF_DEV float tf_min(float a, float b) { return a < b ? a : b; }
+TF_DEV float tf_max(float a, float b) { return a > b ? a : b; }
+TF_DEV int tf_clamp(int x, int a, int b) { return tf_min(tf_max(x, a), b); }
+TF_DEV uint tf_clamp(uint x, uint a, uint b) { return tf_min(tf_max(x, a), b); }
+TF_DEV float tf_clamp(float x, float a, float b) { return tf_min(tf_max(x, a), b); }
+
+// ---- small math helpers (CPP.cpp:108-139) ---------------------------------------------------
+TF_DEV float tf_lerp(float a, float b, float t) { return a + (b - a) * t; }
+TF_DEV float tf_smoothstep(float a, float b, float t) {
+	t = tf_clamp((t - a) / (b - a), 0.0f, 1.0f);
+	return t * t * (3.0f - 2.0f * t);
+}
+TF_DEV float tf_sign(float x) { return x < 0.0f ? -1.0f : 1.0f; }  // sign(0) == +1, as the oracle
+TF_DEV int tf_sign(int x) { return x < 0 ? -1 : 1; }
+TF_DEV uint tf_reversebits(uint x) { return __brev(x); }
+TF_DEV int tf_reversebits(int x) { return (int)__brev((uint)x); }
+TF_DEV float tf_abs(float x) { return fabsf(x); }
+TF_DEV int tf_abs(int x) { return x < 0 ? -x : x; }
+TF_DEV uint tf_abs(uint x) { return x; }
+
+// libm-backed ops: the oracle falls through to <cmath> float overloads (CPP.cpp:11 renames sqrt only)
+TF_DEV float tf_ceil(float x) { return ceilf(x); }
+TF_DEV float tf_floor(float x) { return floorf(x); }
+TF_DEV float tf_round(float x) { return roundf(x); }  // half away from zero, like C round()
+TF_DEV float tf_trunc(float x) { return truncf(x); }
+TF_DEV float tf_exp(float x) { return expf(x); }
+TF_DEV float tf_exp2(float x) { return exp2f(x); }
+TF_DEV float tf_log(float x) { return logf(x); }
+TF_DEV float tf_log2(float x) { return log2f(x); }
+TF_DEV float tf_sqrt(float x) { return sqrtf(x); }
+TF_DEV float tf_sin(float x) { return sinf(x); }
+TF_DEV float tf_cos(float x) { return cosf(x); }
+TF_DEV float tf_tan(float x) { return tanf(x); }
+TF_DEV float tf_asin(float x) { return asinf(x); }
+TF_DEV float tf_acos(float x) { return acosf(x); }
+TF_DEV float tf_atan(float x) { return atanf(x); }
+TF_DEV float tf_sinh(float x) { return sinhf(x); }
+TF_DEV float tf_cosh(float x) { return coshf(x); }
+TF_DEV float tf_tanh(float x) { return tanhf(x); }
+TF_DEV float tf_pow(float a, float b) { return powf(a, b); }
+TF_DEV float tf_atan2(float a, float b) { return atan2f(a, b); }
+TF_DEV float tf_fma(float a, float b, float c) { return fmaf(a, b, c); }
+// Ops the op table lists (Operations.cpp:150-173) but the C++ helper header never defines, so they do
+// not compile on the oracle ("parity unpinned"); defined here with their HLSL/GLSL meaning.
+TF_DEV float tf_frac(float x) { return x - floorf(x); }
+TF_DEV float tf_rcp(float x) { return 1.0f / x; }
+TF_DEV float tf_rsqrt(float x) { return 1.0f / sqrtf(x); }
+TF_DEV float tf_step(float edge, float x) { return x >= edge ? 1.0f : 0.0f; }
+TF_DEV float tf_modf(float a, float b) { return a - b * floorf(a / b); }  // GLSL mod (GLSL.cpp:11)
+
+// ---- pcg hash (CPP.cpp:261-271) --------------------------------------------------------------
+TF_DEV uint tf_pcg(uint v) {
+	uint state = v * 747796405u + 2891336453u;
+	uint word = ((state >> ((state >> 28u) + 4u)) ^ state) * 277803737u;
+	return (word >> 22u) ^ word;
+}
+TF_DEV float tf_pcgf(uint v) { return (float)tf_pcg(v) / (float)0xffffffffu; }
+
+// ---- barrier: a real one (the oracle's is a no-op, CPP.cpp:259) -------------------------------
+TF_DEV void tf_group_barrier() { __syncthreads(); }
+
+// ---- atomics on word buffers (CPP.cpp:141-257).  `mem` is the uint buffer (global or shared),
+// reinterpret per element type.  Float add is the native red/atom.add.f32, not a CAS loop. --------
+TF_DEV void tf_atomic_add(uint* mem, int a, uint v) { atomicAdd(mem + a, v); }
+TF_DEV void tf_atomic_add(uint* mem, int a, int v) { atomicAdd((int*)mem + a, v); }
+TF_DEV void tf_atomic_add(uint* mem, int a, float v) { atomicAdd((float*)mem + a, v); }
+TF_DEV uint tf_atomic_add_prev(uint* mem, int a, uint v) { return atomicAdd(mem + a, v); }
+TF_DEV int tf_atomic_add_prev(uint* mem, int a, int v) { return atomicAdd((int*)mem + a, v); }
+TF_DEV float tf_atomic_add_prev(uint* mem, int a, float v) { return atomicAdd((float*)mem + a, v); }
+TF_DEV void tf_atomic_min(uint* mem, int a, uint v) { atomicMin(mem + a, v); }
+TF_DEV void tf_atomic_min(uint* mem, int a, int v) { atomicMin((int*)mem + a, v); }
+TF_DEV void tf_atomic_max(uint* mem, int a, uint v) { atomicMax(mem + a, v); }
+TF_DEV void tf_atomic_max(uint* mem, int a, int v) { atomicMax((int*)mem + a, v); }
+TF_DEV void tf_atomic_min(uint* mem, int a, float v) {
+	uint* p = mem + a;
+	uint cur = *p;
+	for (;;) {
+		float goal = tf_min(__uint_as_float(cur), v);
+		uint seen = atomicCAS(p, cur, __float_as_uint(goal));
+		if (seen == cur) break;
+		cur = seen;
+	}
+}
+TF_DEV void tf_atomic_max(uint* mem, int a, float v) {
+	uint* p = mem + a;
+	uint cur = *p;
+	for (;;) {
+		float goal = tf_max(__uint_as_float(cur), v);
+		uint seen = atomicCAS(p, cur, __float_as_uint(goal));
+		if (seen == cur) break;
+		cur = seen;
+	}
+}
+TF_DEV void tf_atomic_and(uint* mem, int a, uint v) { atomicAnd(mem + a, v); }
+TF_DEV void tf_atomic_and(uint* mem, int a, int v) {
+#if TF_QUIRK_INT_AND_IS_OR
+	atomicOr((int*)mem + a, v);
+#else
+	atomicAnd((int*)mem + a, v);
+#endif
+}
+TF_DEV void tf_atomic_or(uint* mem, int a, uint v) { atomicOr(mem + a, v); }
+TF_DEV void tf_atomic_or(uint* mem, int a, int v) { atomicOr((int*)mem + a, v); }
+TF_DEV void tf_atomic_xor(uint* mem, int a, uint v) { atomicXor(mem + a, v); }
+TF_DEV void tf_atomic_xor(uint* mem, int a, int v) { atomicXor((int*)mem + a, v); }
+
+// `discard` keyword op (Operations.cpp:33): end this thread.
+#define discard return

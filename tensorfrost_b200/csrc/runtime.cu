@@ -1,0 +1,664 @@
+// libtfcuda runtime: device/stream lifecycle, device buffers + pool, the TFRuntime callback table,
+// NVRTC compilation of emitted kernels and their dispatch through the CUDA driver API.
+//
+// Reference counterparts (paths relative to the reference root):
+//   InitializeBackend                       TensorFrost/Backend/Backend.cpp:10-73
+//   Allocator..Region callbacks             TensorFrost/Backend/Backend.cpp:96-133
+//   TensorMemoryManager pool                TensorFrost/Backend/TensorMemory.cpp:29-224
+//   CpuMemoryManager / TFCPUBuffer          TensorFrost/Backend/Backends/CPU/Memory.h:18-59
+//   CompileKernels / OpenGLKernelManager    TensorFrost/Backend/Backend.cpp:75-94, Backends/OpenGL/KernelManager.h:73-159
+// Design differences: everything is ordered on ONE CUDA stream and only tf.read / readback synchronise;
+// buffers come from the stream-ordered CUDA memory pool (cudaMallocAsync) so neither allocation nor
+// release ever stalls the device; kernels of a program are compiled in parallel NVRTC chunks straight
+// to sm_100a cubins and cached on disk.
+#include <nvrtc.h>
+#include <nvtx3/nvToolsExt.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "tfcuda_internal.h"
+
+namespace tfcuda {
+
+static State g_state;
+static thread_local std::string g_error;
+static std::string g_error_shared;
+static std::mutex g_error_mutex;
+
+State& state() { return g_state; }
+
+void set_error(const std::string& msg) {
+	g_error = msg;
+	std::lock_guard<std::mutex> lock(g_error_mutex);
+	g_error_shared = msg;
+}
+
+std::string cuda_err(cudaError_t e) {
+	return std::string(cudaGetErrorName(e)) + " (" + cudaGetErrorString(e) + ")";
+}
+
+void require_init() {
+	if (!g_state.initialized) {
+		throw std::runtime_error("tfcuda: backend not initialised (tfcuda_init failed or was never called); there is no CPU fallback");
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// Buffer pool used by the TFRuntime.alloc/dealloc callbacks (stand-alone use of the C-ABI).  Exact
+// size-class free lists: programs have static shapes, so a released buffer is almost always requested
+// again with the same size on the next step.  Capacity is rounded up to 64 words (256 B) so near-equal
+// sizes share a class.  The device memory itself comes from cudaMallocAsync.
+// ------------------------------------------------------------------------------------------------
+struct Pool {
+	std::unordered_map<size_t, std::vector<Buffer*>> free_lists;
+	size_t allocated_words = 0;
+	size_t unused_words = 0;
+};
+static Pool g_pool;
+
+static size_t round_words(size_t words) { return (words + 63) & ~size_t(63); }
+
+static Buffer* create_buffer(size_t words) {
+	require_init();
+	if (words == 0) throw std::invalid_argument("tfcuda: trying to allocate a buffer with size 0");
+	void* p = nullptr;
+	cudaError_t e = cudaMallocAsync(&p, words * sizeof(uint32_t), g_state.stream);
+	if (e != cudaSuccess) {
+		// the pool may be holding memory another size class could use: trim and retry once
+		cudaStreamSynchronize(g_state.stream);
+		cudaMemPool_t mp;
+		if (cudaDeviceGetDefaultMemPool(&mp, g_state.device) == cudaSuccess) cudaMemPoolTrimTo(mp, 0);
+		(void)cudaGetLastError();
+		e = cudaMallocAsync(&p, words * sizeof(uint32_t), g_state.stream);
+	}
+	if (e != cudaSuccess) {
+		std::string m = "tfcuda: device allocation of " + std::to_string(words * 4) + " bytes failed: " + cuda_err(e);
+		set_error(m);
+		throw std::runtime_error(m);
+	}
+	Buffer* b = new Buffer();
+	b->base.size = words;
+	b->dptr = reinterpret_cast<uint64_t>(p);
+	g_pool.allocated_words += words;
+	return b;
+}
+
+static void destroy_buffer(Buffer* b) {
+	if (!b) return;
+	if (b->dptr && g_state.initialized) cudaFreeAsync(reinterpret_cast<void*>(b->dptr), g_state.stream);
+	g_pool.allocated_words -= b->base.size;
+	delete b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// TFRuntime callbacks
+// ------------------------------------------------------------------------------------------------
+static TFTensor rt_alloc(const char* name, const size_t* shape, size_t dim, TFDataFormat fmt, void*) {
+	size_t words = 1;
+	for (size_t i = 0; i < dim; i++) words *= shape[i];
+	if (words == 0) throw std::invalid_argument(std::string("tfcuda: tensor ") + (name ? name : "?") + " has size 0");
+	size_t cls = round_words(words);
+	Buffer* b = nullptr;
+	auto it = g_pool.free_lists.find(cls);
+	if (it != g_pool.free_lists.end() && !it->second.empty()) {
+		b = it->second.back();
+		it->second.pop_back();
+		g_pool.unused_words -= b->base.size;
+	} else {
+		b = create_buffer(cls);
+	}
+	b->base.used_size = words;
+	b->base.time_since_used = 0;
+	b->base.read_only = false;
+	b->base.up_to_date = false;
+	b->base.name = name;
+	size_t* shape_copy = new size_t[dim ? dim : 1];
+	for (size_t i = 0; i < dim; i++) shape_copy[i] = shape[i];
+	TFTensor t;
+	t.buffer = &b->base;
+	t.format = fmt;
+	t.dim = dim;
+	t.shape = shape_copy;
+	return t;
+}
+
+static void rt_dealloc(TFTensor t, void*) {
+	if (!t.buffer) return;
+	Buffer* b = reinterpret_cast<Buffer*>(t.buffer);
+	b->base.used_size = 0;
+	b->base.name = "none";
+	g_pool.free_lists[b->base.size].push_back(b);
+	g_pool.unused_words += b->base.size;
+}
+
+static uint32_t rt_readback(TFTensor t, size_t index, void*) {
+	require_init();
+	if (!t.buffer || index >= t.buffer->size) throw std::out_of_range("tfcuda: tf.read index out of range");
+	TFCUDA_THROW(cudaMemcpyAsync(g_state.pinned_word, reinterpret_cast<const void*>(dptr_of(t.buffer) + index * 4), 4,
+	                             cudaMemcpyDeviceToHost, g_state.stream));
+	TFCUDA_THROW(cudaStreamSynchronize(g_state.stream));
+	return *g_state.pinned_word;
+}
+
+static void rt_writeback(TFTensor t, size_t index, uint32_t value, void*) {
+	require_init();
+	if (!t.buffer || index >= t.buffer->size) throw std::out_of_range("tfcuda: tf.write index out of range");
+	// a 32-bit fill is stream ordered and needs no host staging
+	int rc = tfcuda_memset32(dptr_of(t.buffer) + index * 4, value, 1);
+	if (rc) throw std::runtime_error(std::string("tfcuda: tf.write failed: ") + tfcuda_last_error());
+}
+
+static void rt_dispatch(TFDispatchInfo info, void*) {
+	if (tfcuda_dispatch(&info)) throw std::runtime_error(std::string("tfcuda: dispatch of kernel ") + std::to_string(info.kernel_id) + " failed: " + tfcuda_last_error());
+}
+
+static void rt_region(const char* name, bool begin, void*) {
+	if (begin) nvtxRangePushA(name ? name : "region");
+	else nvtxRangePop();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel registry
+// ------------------------------------------------------------------------------------------------
+struct KernelEntry {
+	CUfunction fn = nullptr;
+	unsigned group[3] = {1, 1, 1};
+	unsigned n_mem = 0;
+	unsigned n_var = 0;
+	unsigned library_op = 0;
+	std::string entry;
+};
+static std::vector<KernelEntry> g_kernels;
+static std::vector<CUmodule> g_modules;
+
+static uint64_t fnv1a(const std::string& s, uint64_t h = 1469598103934665603ull) {
+	for (unsigned char c : s) {
+		h ^= c;
+		h *= 1099511628211ull;
+	}
+	return h;
+}
+
+static std::string cache_dir() {
+	const char* env = getenv("TFCUDA_CACHE_DIR");
+	std::string dir = env ? env : ("/tmp/tfcuda_cache_" + std::to_string((long)getuid()));
+	mkdir(dir.c_str(), 0700);
+	return dir;
+}
+
+static bool read_file(const std::string& path, std::string& out) {
+	std::ifstream f(path, std::ios::binary);
+	if (!f) return false;
+	std::stringstream ss;
+	ss << f.rdbuf();
+	out = ss.str();
+	return !out.empty();
+}
+
+static void write_file_atomic(const std::string& path, const std::string& data) {
+	std::string tmp = path + ".tmp" + std::to_string((long)getpid());
+	{
+		std::ofstream f(tmp, std::ios::binary);
+		if (!f) return;
+		f.write(data.data(), (std::streamsize)data.size());
+	}
+	rename(tmp.c_str(), path.c_str());
+}
+
+static const char kPrelude[] =
+#include "prelude_embed.inc"
+    ;
+
+struct Chunk {
+	std::string source;
+	std::string cubin;
+	std::string log;
+	bool ok = false;
+	bool from_cache = false;
+};
+
+static void compile_chunk(Chunk& c, const std::vector<std::string>& opts, bool use_cache) {
+	std::string key_src = c.source;
+	for (auto& o : opts) key_src += "\x01" + o;
+	int maj = 0, min = 0;
+	nvrtcVersion(&maj, &min);
+	key_src += "\x01nvrtc" + std::to_string(maj) + "." + std::to_string(min);
+	char name[64];
+	snprintf(name, sizeof(name), "%016llx.cubin", (unsigned long long)fnv1a(key_src));
+	std::string path = use_cache ? cache_dir() + "/" + name : std::string();
+	if (use_cache && read_file(path, c.cubin)) {
+		c.ok = true;
+		c.from_cache = true;
+		return;
+	}
+	nvrtcProgram prog = nullptr;
+	nvrtcResult r = nvrtcCreateProgram(&prog, c.source.c_str(), "tf_kernels.cu", 0, nullptr, nullptr);
+	if (r != NVRTC_SUCCESS) {
+		c.log = std::string("nvrtcCreateProgram: ") + nvrtcGetErrorString(r);
+		return;
+	}
+	std::vector<const char*> copts;
+	for (auto& o : opts) copts.push_back(o.c_str());
+	r = nvrtcCompileProgram(prog, (int)copts.size(), copts.data());
+	size_t log_size = 0;
+	nvrtcGetProgramLogSize(prog, &log_size);
+	if (log_size > 1) {
+		c.log.resize(log_size);
+		nvrtcGetProgramLog(prog, c.log.data());
+	}
+	if (r != NVRTC_SUCCESS) {
+		c.log = std::string("nvrtcCompileProgram: ") + nvrtcGetErrorString(r) + "\n" + c.log;
+		nvrtcDestroyProgram(&prog);
+		return;
+	}
+	size_t size = 0;
+	nvrtcGetCUBINSize(prog, &size);
+	c.cubin.resize(size);
+	nvrtcGetCUBIN(prog, c.cubin.data());
+	nvrtcDestroyProgram(&prog);
+	c.ok = size > 0;
+	if (!c.ok) c.log += "\nempty cubin";
+	if (c.ok && use_cache) write_file_atomic(path, c.cubin);
+}
+
+static std::string drv_err(CUresult r) {
+	const char* s = nullptr;
+	if (g_state.drv.GetErrorString) g_state.drv.GetErrorString(r, &s);
+	return s ? s : ("CUresult " + std::to_string((int)r));
+}
+
+template <typename T>
+static bool load_entry(const char* sym, T& fn) {
+	void* p = nullptr;
+	cudaDriverEntryPointQueryResult q;
+	cudaError_t e = cudaGetDriverEntryPoint(sym, &p, cudaEnableDefault, &q);
+	if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+		set_error(std::string("cannot resolve driver entry point ") + sym);
+		return false;
+	}
+	fn = reinterpret_cast<T>(p);
+	return true;
+}
+
+}  // namespace tfcuda
+
+using namespace tfcuda;
+
+// ================================================================================================
+// C-ABI
+// ================================================================================================
+extern "C" {
+
+const char* tfcuda_last_error(void) {
+	if (!g_error.empty()) return g_error.c_str();
+	std::lock_guard<std::mutex> lock(g_error_mutex);
+	g_error = g_error_shared;
+	return g_error.c_str();
+}
+
+const char* tfcuda_prelude(void) { return kPrelude; }
+
+int tfcuda_is_initialized(void) { return g_state.initialized ? 1 : 0; }
+
+int tfcuda_init(int device) {
+	if (g_state.initialized) {
+		if (device >= 0 && device != g_state.device) {
+			set_error("tfcuda_init: already initialised on device " + std::to_string(g_state.device) + " (one device per process)");
+			return 1;
+		}
+		return 0;
+	}
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0) {
+		(void)cudaGetLastError();
+		set_error("tfcuda_init: no CUDA device available (" + (e != cudaSuccess ? cuda_err(e) : std::string("device count 0")) + "); this backend has no CPU fallback");
+		return 1;
+	}
+	if (device < 0) {
+		const char* lr = getenv("LOCAL_RANK");
+		device = lr ? atoi(lr) % count : 0;
+	}
+	if (device >= count) {
+		set_error("tfcuda_init: device " + std::to_string(device) + " out of range, " + std::to_string(count) + " visible");
+		return 1;
+	}
+	TFCUDA_CHECK(cudaSetDevice(device));
+	TFCUDA_CHECK(cudaFree(0));  // force primary-context creation
+	cudaDeviceProp prop;
+	TFCUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+	g_state.device = device;
+	g_state.sm_count = prop.multiProcessorCount;
+	g_state.device_name = prop.name;
+	if (prop.major < 10 && !getenv("TFCUDA_ALLOW_ANY_ARCH")) {
+		set_error("tfcuda_init: device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + "; this backend is built for sm_100a (B200) only");
+		return 1;
+	}
+	DriverApi& d = g_state.drv;
+	if (!load_entry("cuModuleLoadData", d.ModuleLoadData) || !load_entry("cuModuleUnload", d.ModuleUnload) ||
+	    !load_entry("cuModuleGetFunction", d.ModuleGetFunction) || !load_entry("cuLaunchKernel", d.LaunchKernel) ||
+	    !load_entry("cuGetErrorString", d.GetErrorString) || !load_entry("cuFuncGetAttribute", d.FuncGetAttribute)) {
+		return 1;
+	}
+	TFCUDA_CHECK(cudaStreamCreateWithFlags(&g_state.stream, cudaStreamNonBlocking));
+	TFCUDA_CHECK(cudaMallocHost(&g_state.pinned_word, 64));
+	TFCUDA_CHECK(cudaEventCreate(&g_state.ev_begin));
+	TFCUDA_CHECK(cudaEventCreate(&g_state.ev_end));
+	// keep freed blocks in the stream-ordered pool instead of returning them to the OS at every sync
+	cudaMemPool_t mp;
+	TFCUDA_CHECK(cudaDeviceGetDefaultMemPool(&mp, device));
+	uint64_t threshold = UINT64_MAX;
+	TFCUDA_CHECK(cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &threshold));
+	g_state.initialized = true;
+	return 0;
+}
+
+int tfcuda_shutdown(void) {
+	if (!g_state.initialized) return 0;
+	cudaStreamSynchronize(g_state.stream);
+	for (auto& kv : g_pool.free_lists)
+		for (Buffer* b : kv.second) destroy_buffer(b);
+	g_pool.free_lists.clear();
+	g_pool.unused_words = 0;
+	for (CUmodule m : g_modules) g_state.drv.ModuleUnload(m);
+	g_modules.clear();
+	g_kernels.clear();
+	cudaEventDestroy(g_state.ev_begin);
+	cudaEventDestroy(g_state.ev_end);
+	cudaFreeHost(g_state.pinned_word);
+	cudaStreamDestroy(g_state.stream);
+	g_state = State();
+	return 0;
+}
+
+int tfcuda_device_sm_count(void) { return g_state.sm_count; }
+const char* tfcuda_device_name(void) { return g_state.device_name.c_str(); }
+void* tfcuda_stream(void) { return g_state.stream; }
+
+int tfcuda_sync(void) {
+	if (!g_state.initialized) {
+		set_error("tfcuda_sync: not initialised");
+		return 1;
+	}
+	TFCUDA_CHECK(cudaStreamSynchronize(g_state.stream));
+	return 0;
+}
+
+TFRuntime tfcuda_runtime(void) {
+	TFRuntime rt;
+	rt.alloc = rt_alloc;
+	rt.dealloc = rt_dealloc;
+	rt.readback = rt_readback;
+	rt.writeback = rt_writeback;
+	rt.dispatch = rt_dispatch;
+	rt.region = rt_region;
+	rt.custom_data = nullptr;
+	return rt;
+}
+
+// ---- buffers ------------------------------------------------------------------------------------
+TFBuffer* tfcuda_buffer_create(size_t words) {
+	try {
+		return &create_buffer(words)->base;
+	} catch (const std::exception& e) {
+		set_error(e.what());
+		return nullptr;
+	}
+}
+
+void tfcuda_buffer_destroy(TFBuffer* buffer) { destroy_buffer(reinterpret_cast<Buffer*>(buffer)); }
+
+uint64_t tfcuda_buffer_device_ptr(const TFBuffer* buffer) { return buffer ? dptr_of(buffer) : 0; }
+
+int tfcuda_buffer_write(TFBuffer* buffer, size_t word_offset, const uint32_t* src, size_t words) {
+	if (!buffer || word_offset + words > buffer->size) {
+		set_error("tfcuda_buffer_write: range exceeds buffer");
+		return 1;
+	}
+	return tfcuda_memcpy_h2d(dptr_of(buffer) + word_offset * 4, src, words * 4);
+}
+
+int tfcuda_buffer_read(const TFBuffer* buffer, size_t word_offset, uint32_t* dst, size_t words) {
+	if (!buffer || word_offset + words > buffer->size) {
+		set_error("tfcuda_buffer_read: range exceeds buffer");
+		return 1;
+	}
+	return tfcuda_memcpy_d2h(dst, dptr_of(buffer) + word_offset * 4, words * 4);
+}
+
+int tfcuda_memcpy_h2d(uint64_t dst, const void* src, size_t bytes) {
+	if (!g_state.initialized) { set_error("tfcuda: not initialised"); return 1; }
+	if (bytes == 0) return 0;
+	TFCUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<void*>(dst), src, bytes, cudaMemcpyHostToDevice, g_state.stream));
+	// pageable sources are consumed before the call returns; pinned ones are not, so order the host too
+	TFCUDA_CHECK(cudaStreamSynchronize(g_state.stream));
+	return 0;
+}
+
+int tfcuda_memcpy_d2h(void* dst, uint64_t src, size_t bytes) {
+	if (!g_state.initialized) { set_error("tfcuda: not initialised"); return 1; }
+	if (bytes == 0) return 0;
+	TFCUDA_CHECK(cudaMemcpyAsync(dst, reinterpret_cast<const void*>(src), bytes, cudaMemcpyDeviceToHost, g_state.stream));
+	TFCUDA_CHECK(cudaStreamSynchronize(g_state.stream));
+	return 0;
+}
+
+int tfcuda_memcpy_d2d(uint64_t dst, uint64_t src, size_t bytes) {
+	if (!g_state.initialized) { set_error("tfcuda: not initialised"); return 1; }
+	if (bytes == 0) return 0;
+	TFCUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<void*>(dst), reinterpret_cast<const void*>(src), bytes, cudaMemcpyDeviceToDevice, g_state.stream));
+	return 0;
+}
+
+uint64_t tfcuda_malloc(size_t bytes) {
+	if (!g_state.initialized) { set_error("tfcuda: not initialised"); return 0; }
+	void* p = nullptr;
+	cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 4, g_state.stream);
+	if (e != cudaSuccess) {
+		set_error("tfcuda_malloc(" + std::to_string(bytes) + "): " + cuda_err(e));
+		return 0;
+	}
+	return reinterpret_cast<uint64_t>(p);
+}
+
+int tfcuda_free(uint64_t ptr) {
+	if (!ptr) return 0;
+	TFCUDA_CHECK(cudaFreeAsync(reinterpret_cast<void*>(ptr), g_state.stream));
+	return 0;
+}
+
+size_t tfcuda_pool_allocated_words(void) { return g_pool.allocated_words; }
+size_t tfcuda_pool_unused_words(void) { return g_pool.unused_words; }
+
+// ---- kernels ------------------------------------------------------------------------------------
+static std::vector<std::string> nvrtc_options(const char* options) {
+	std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-default-device", "-lineinfo"};
+	if (options) {
+		std::istringstream ss(options);
+		std::string tok;
+		while (ss >> tok) opts.push_back(tok);
+	}
+	return opts;
+}
+
+int tfcuda_nvrtc_check(const char* source, const char* options) {
+	Chunk c;
+	c.source = std::string(kPrelude) + "\n" + (source ? source : "");
+	compile_chunk(c, nvrtc_options(options), false);
+	if (!c.ok) {
+		set_error("NVRTC: " + c.log);
+		return 2;
+	}
+	return 0;
+}
+
+int tfcuda_compile_kernels(const TFCudaKernelSource* kernels, size_t count, const char* options) {
+	if (!g_state.initialized) { set_error("tfcuda_compile_kernels: not initialised"); return 1; }
+	if (count == 0) return 0;
+
+	std::vector<std::string> opts = nvrtc_options(options);
+	bool use_cache = getenv("TFCUDA_NO_CACHE") == nullptr;
+
+	// chunk the emitted kernels; each chunk is one NVRTC translation unit = prelude + kernels
+	const size_t kPerChunk = 12;
+	std::vector<size_t> emitted;
+	for (size_t i = 0; i < count; i++)
+		if (kernels[i].library_op == 0) emitted.push_back(i);
+	std::vector<Chunk> chunks((emitted.size() + kPerChunk - 1) / kPerChunk);
+	for (size_t c = 0; c < chunks.size(); c++) {
+		std::string& src = chunks[c].source;
+		src = kPrelude;
+		for (size_t j = c * kPerChunk; j < std::min(emitted.size(), (c + 1) * kPerChunk); j++) {
+			src += "\n";
+			src += kernels[emitted[j]].source;
+		}
+	}
+	unsigned hw = std::thread::hardware_concurrency();
+	size_t n_threads = std::min<size_t>(chunks.size(), hw ? hw : 4);
+	std::atomic<size_t> next{0};
+	auto worker = [&]() {
+		for (;;) {
+			size_t i = next.fetch_add(1);
+			if (i >= chunks.size()) break;
+			compile_chunk(chunks[i], opts, use_cache);
+		}
+	};
+	if (n_threads <= 1) {
+		worker();
+	} else {
+		std::vector<std::thread> threads;
+		for (size_t t = 0; t < n_threads; t++) threads.emplace_back(worker);
+		for (auto& t : threads) t.join();
+	}
+
+	for (size_t c = 0; c < chunks.size(); c++) {
+		if (!chunks[c].ok) {
+			set_error("NVRTC failed for kernel chunk " + std::to_string(c) + ":\n" + chunks[c].log + "\n---- source ----\n" + chunks[c].source.substr(strlen(kPrelude)));
+			return 2;
+		}
+	}
+
+	std::vector<CUmodule> mods(chunks.size(), nullptr);
+	for (size_t c = 0; c < chunks.size(); c++) {
+		CUresult r = g_state.drv.ModuleLoadData(&mods[c], chunks[c].cubin.data());
+		if (r != CUDA_SUCCESS) {
+			set_error("cuModuleLoadData: " + drv_err(r));
+			return 3;
+		}
+		g_modules.push_back(mods[c]);
+	}
+	for (size_t i = 0; i < count; i++) {
+		const TFCudaKernelSource& k = kernels[i];
+		if (k.kernel_id >= g_kernels.size()) g_kernels.resize(k.kernel_id + 1);
+		KernelEntry& e = g_kernels[k.kernel_id];
+		e = KernelEntry();
+		for (int d = 0; d < 3; d++) e.group[d] = k.group[d] ? k.group[d] : 1;
+		e.n_mem = k.n_mem;
+		e.n_var = k.n_var;
+		e.library_op = k.library_op;
+		e.entry = k.entry ? k.entry : "";
+	}
+	for (size_t j = 0; j < emitted.size(); j++) {
+		const TFCudaKernelSource& k = kernels[emitted[j]];
+		KernelEntry& e = g_kernels[k.kernel_id];
+		CUresult r = g_state.drv.ModuleGetFunction(&e.fn, mods[j / kPerChunk], k.entry);
+		if (r != CUDA_SUCCESS) {
+			set_error(std::string("cuModuleGetFunction(") + k.entry + "): " + drv_err(r));
+			return 4;
+		}
+	}
+	return 0;
+}
+
+int tfcuda_launch(size_t kernel_id, const uint64_t* mem, size_t n_mem, const uint32_t* vars, size_t n_var, size_t work_group_count) {
+	if (!g_state.initialized) { set_error("tfcuda_launch: not initialised"); return 1; }
+	if (kernel_id >= g_kernels.size() || (!g_kernels[kernel_id].fn && !g_kernels[kernel_id].library_op)) {
+		set_error("tfcuda_launch: kernel " + std::to_string(kernel_id) + " was never compiled");
+		return 1;
+	}
+	KernelEntry& e = g_kernels[kernel_id];
+	if (n_mem != e.n_mem || n_var != e.n_var) {
+		set_error("tfcuda_launch: kernel " + std::to_string(kernel_id) + " expects " + std::to_string(e.n_mem) + " buffers / " + std::to_string(e.n_var) +
+		          " variables, got " + std::to_string(n_mem) + " / " + std::to_string(n_var));
+		return 1;
+	}
+	if (work_group_count == 0) return 0;
+	// argument block = { uint* mem[n_mem]; uint var[n_var]; } passed by value as the single kernel parameter
+	alignas(8) unsigned char block[4096];
+	size_t bytes = n_mem * 8 + n_var * 4;
+	if (bytes > sizeof(block)) {
+		set_error("tfcuda_launch: argument block too large");
+		return 1;
+	}
+	memcpy(block, mem, n_mem * 8);
+	memcpy(block + n_mem * 8, vars, n_var * 4);
+	uint32_t* offset_word = n_var ? reinterpret_cast<uint32_t*>(block + n_mem * 8 + (n_var - 1) * 4) : nullptr;
+	void* params[1] = {block};
+	// grid.x is limited to 2^31-1: larger dispatches are split with the _kernel_block_offset word
+	const size_t kMaxGrid = 0x7fffffffull;
+	size_t done = 0;
+	while (done < work_group_count) {
+		size_t now = std::min(kMaxGrid, work_group_count - done);
+		if (offset_word) *offset_word = vars[n_var - 1] + (uint32_t)done;
+		CUresult r = g_state.drv.LaunchKernel(e.fn, (unsigned)now, 1, 1, e.group[0], e.group[1], e.group[2], 0,
+		                                      (CUstream)g_state.stream, params, nullptr);
+		if (r != CUDA_SUCCESS) {
+			set_error("cuLaunchKernel(" + e.entry + ", grid=" + std::to_string(now) + ", block=" + std::to_string(e.group[0]) + "x" +
+			          std::to_string(e.group[1]) + "x" + std::to_string(e.group[2]) + "): " + drv_err(r));
+			return 1;
+		}
+		g_state.launches++;
+		done += now;
+	}
+	return 0;
+}
+
+int tfcuda_dispatch(const TFDispatchInfo* info) {
+	uint64_t ptrs[256];
+	size_t n = info->read_write_count + info->read_only_count;
+	if (n > 256) { set_error("tfcuda_dispatch: too many buffers"); return 1; }
+	for (size_t i = 0; i < info->read_write_count; i++) ptrs[i] = dptr_of(info->read_write_tensors[i].buffer);
+	for (size_t i = 0; i < info->read_only_count; i++) ptrs[info->read_write_count + i] = dptr_of(info->read_only_tensors[i].buffer);
+	return tfcuda_launch(info->kernel_id, ptrs, n, info->variables, info->variable_count, info->work_group_count);
+}
+
+uint64_t tfcuda_launch_count(void) { return g_state.launches; }
+
+int tfcuda_timer_begin(void) {
+	if (!g_state.initialized) { set_error("tfcuda: not initialised"); return 1; }
+	TFCUDA_CHECK(cudaEventRecord(g_state.ev_begin, g_state.stream));
+	return 0;
+}
+
+int tfcuda_timer_end(float* ms) {
+	if (!g_state.initialized) { set_error("tfcuda: not initialised"); return 1; }
+	TFCUDA_CHECK(cudaEventRecord(g_state.ev_end, g_state.stream));
+	TFCUDA_CHECK(cudaEventSynchronize(g_state.ev_end));
+	TFCUDA_CHECK(cudaEventElapsedTime(ms, g_state.ev_begin, g_state.ev_end));
+	return 0;
+}
+
+}  // extern "C"
+
+// tiny utility kernel: 32-bit fill (tf.write and buffer clears)
+__global__ void tfcuda_fill32_kernel(uint32_t* p, uint32_t v, size_t n) {
+	size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+	size_t stride = (size_t)gridDim.x * blockDim.x;
+	for (; i < n; i += stride) p[i] = v;
+}
+
+extern "C" int tfcuda_memset32(uint64_t dst, uint32_t value, size_t words) {
+	if (!g_state.initialized) { set_error("tfcuda: not initialised"); return 1; }
+	if (words == 0) return 0;
+	size_t blocks = std::min<size_t>((words + 255) / 256, (size_t)g_state.sm_count * 8);
+	tfcuda_fill32_kernel<<<(unsigned)blocks, 256, 0, g_state.stream>>>(reinterpret_cast<uint32_t*>(dst), value, words);
+	return check_launch("tfcuda_memset32");
+}

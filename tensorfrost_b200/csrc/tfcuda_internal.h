@@ -1,0 +1,85 @@
+// Internal shared state of libtfcuda.so (not part of the C-ABI).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/tfcuda.h"
+
+namespace tfcuda {
+
+// Driver-API entry points are resolved through cudaGetDriverEntryPoint so the library has no link-time
+// dependency on libcuda.so.1 (it must load — and export its symbols — on a box without a driver).
+struct DriverApi {
+	CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
+	CUresult (*ModuleUnload)(CUmodule) = nullptr;
+	CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+	CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+	                         unsigned, CUstream, void**, void**) = nullptr;
+	CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+	CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
+};
+
+struct State {
+	bool initialized = false;
+	int device = -1;
+	int sm_count = 0;
+	std::string device_name;
+	cudaStream_t stream = nullptr;
+	DriverApi drv;
+	uint32_t* pinned_word = nullptr;  // 1-word staging for tf.read / tf.write
+	cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+	uint64_t launches = 0;
+};
+
+State& state();
+void set_error(const std::string& msg);
+std::string cuda_err(cudaError_t e);
+
+// The device buffer behind a TFBuffer: TFBuffer must stay the first member so TFBuffer* <-> Buffer* is a cast.
+struct Buffer {
+	TFBuffer base;
+	uint64_t dptr = 0;
+};
+
+inline uint64_t dptr_of(const TFBuffer* b) { return reinterpret_cast<const Buffer*>(b)->dptr; }
+
+void require_init();  // throws std::runtime_error when tfcuda_init has not succeeded
+
+#define TFCUDA_CHECK(expr)                                                                   \
+	do {                                                                                     \
+		cudaError_t _e = (expr);                                                             \
+		if (_e != cudaSuccess) {                                                             \
+			::tfcuda::set_error(std::string(#expr) + ": " + ::tfcuda::cuda_err(_e));         \
+			return 1;                                                                        \
+		}                                                                                    \
+	} while (0)
+
+#define TFCUDA_THROW(expr)                                                                   \
+	do {                                                                                     \
+		cudaError_t _e = (expr);                                                             \
+		if (_e != cudaSuccess) {                                                             \
+			std::string _m = std::string("tfcuda: ") + #expr + ": " + ::tfcuda::cuda_err(_e); \
+			::tfcuda::set_error(_m);                                                         \
+			throw std::runtime_error(_m);                                                    \
+		}                                                                                    \
+	} while (0)
+
+// library kernels report launch errors through this
+inline int check_launch(const char* what) {
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) {
+		set_error(std::string(what) + ": " + cuda_err(e));
+		return 1;
+	}
+	state().launches++;
+	return 0;
+}
+
+}  // namespace tfcuda

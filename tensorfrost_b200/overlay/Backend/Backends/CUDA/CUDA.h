@@ -1,0 +1,59 @@
+// CUDA (B200, sm_100a) backend for TensorFrost: the third sibling of Backends/CPU and Backends/OpenGL.
+//
+// Added to the reference tree as TensorFrost/Backend/Backends/CUDA/CUDA.h.  It is deliberately thin: all
+// device work lives behind the C-ABI of libtfcuda.so (include/tfcuda.h); this header only adapts that ABI
+// to the reference's three C++ extension points:
+//   TensorMemoryManager::{CreateBuffer,DeleteBuffer}          Backend/TensorMemory.h:112-125
+//   TFBufferTemplate::{UpdateName,SetDataAtOffset,GetDataAtOffset}   Backend/TensorMemory.h:74-88
+//   KernelManager::DispatchKernel (+ a CompileProgram hook)   Backend/KernelManager.h:16-30
+// mirroring what Backends/CPU/{Memory.h,KernelManager.h} and Backends/OpenGL/{Memory.h,KernelManager.h} do.
+#pragma once
+
+#include <string>
+#include <vector>
+
+#include "../../KernelManager.h"
+#include "../../TensorMemory.h"
+
+namespace TensorFrost {
+
+using namespace std;
+
+// NVRTC flags for emitted kernels (the kernel_compile_options string of tf.initialize)
+extern std::string cudaKernelCompileOptions;
+
+void StartCUDA();
+void StopCUDA();
+void CudaFinish();
+void CudaRegion(const char* name, bool begin);
+
+class TFCudaBuffer : public TFBufferTemplate {
+ public:
+	uint64_t device_ptr = 0;
+	void* handle = nullptr;  // TFBuffer* owned by libtfcuda
+
+	explicit TFCudaBuffer(size_t size);
+	~TFCudaBuffer();
+
+	void UpdateName(const char* new_name) override {
+		if (new_name != nullptr) name = new_name;
+	}
+	void SetDataAtOffset(size_t offset, const vector<uint32_t>& data) override;
+	void GetDataAtOffset(size_t offset, size_t size, uint32_t* data) override;
+	uint64_t GetNative() const { return device_ptr; }
+};
+
+class CudaMemoryManager : public TensorMemoryManager {
+ public:
+	TFBuffer* CreateBuffer(size_t size) override { return new TFCudaBuffer(size); }
+	void DeleteBuffer(TFBuffer* buffer) override { delete (TFCudaBuffer*)buffer; }
+};
+
+class CudaKernelManager : public KernelManager {
+ public:
+	// compiles every kernel of the program in one call (parallel NVRTC chunks inside libtfcuda)
+	void CompileProgram(Program* program);
+	void DispatchKernel(TFDispatchInfo info) override;
+};
+
+}  // namespace TensorFrost

@@ -1,0 +1,207 @@
+// Python surface of the CUDA backend: `CudaDefinitions(m)` is called from PYBIND11_MODULE
+// (Frontend/Python/PybindModule.cpp:96-101 calls the other *Definitions the same way).
+//
+// Nothing here changes an existing tf.* function.  It adds what a device backend needs next to them:
+//   tf.cuda_synchronize / cuda_timer_* / cuda_launch_count   — device-side timing for benchmarks
+//   tf.cuda_tensor(np) / tf.cuda_numpy(t) / tf.cuda_upload   — bulk host<->device copies that skip the
+//        per-element std::function conversion of PyTensorMemory (Frontend/Python/PyTensorMemory.cpp:19-84,
+//        PyTensorMemory.h:30-45); same dtype rules for the 4-byte types, same result objects
+//   tf.cuda_device_ptr(t)                                     — interop (e.g. torch via __cuda_array_interface__)
+//   tf.cuda_comm_* / tf.cuda_allreduce                        — the data-parallel gradient exchange
+//   tf.cuda_radix_sort / cuda_reduce / cuda_prefix_sum / cuda_matmul / cuda_scatter_add / cuda_nbody_step
+//        — the hand-written library kernels on TensorMemory objects
+#include <Frontend/Python/PyTensor.h>
+#include <Frontend/Python/PyTensorMemory.h>
+
+#include "CUDA.h"
+
+#define TFCUDA_NO_ABI_STRUCTS
+namespace tfcuda_abi {
+using TensorFrost::TFBuffer;
+using TensorFrost::TFDataFormat;
+using TensorFrost::TFDispatchInfo;
+using TensorFrost::TFRuntime;
+using TensorFrost::TFTensor;
+#include "tfcuda.h"
+}  // namespace tfcuda_abi
+using namespace tfcuda_abi;
+
+namespace TensorFrost {
+
+namespace {
+
+void RequireCuda(const char* what) {
+	if (current_backend != BackendType::CUDA) {
+		throw std::runtime_error(std::string(what) + " requires tf.initialize(tf.cuda)");
+	}
+}
+
+void Check(int rc, const char* what) {
+	if (rc != 0) throw std::runtime_error(std::string(what) + ": " + tfcuda_last_error());
+}
+
+uint64_t DevPtr(const PyTensorMemory& t) { return ((TFCudaBuffer*)t.tensor_->buffer)->GetNative(); }
+
+TFDataFormat FormatOf(const py::buffer_info& info) {
+	if (info.itemsize != 4) throw std::runtime_error("cuda_tensor: only 4-byte dtypes (float32/int32/uint32) take the bulk path");
+	switch (info.format[0]) {
+		case 'f': return TFTypeFloat32;
+		case 'i': case 'l': return TFTypeInt32;
+		case 'I': case 'L': return TFTypeUint32;
+		default: throw std::runtime_error("cuda_tensor: unsupported dtype format " + info.format);
+	}
+}
+
+PyTensorMemory* NewLike(const PyTensorMemory& t, TFDataFormat fmt) {
+	return new PyTensorMemory(global_memory_manager->AllocateTensor(t.Shape(), fmt));
+}
+
+}  // namespace
+
+void CudaDefinitions(py::module& m) {
+	m.def("cuda_synchronize", []() { RequireCuda("cuda_synchronize"); CudaFinish(); }, "Wait for all queued device work");
+	m.def("cuda_launch_count", []() { return tfcuda_launch_count(); }, "Kernels launched since initialisation");
+	m.def("cuda_timer_begin", []() { Check(tfcuda_timer_begin(), "cuda_timer_begin"); });
+	m.def("cuda_timer_end", []() { float ms = 0; Check(tfcuda_timer_end(&ms), "cuda_timer_end"); return ms; },
+	      "Milliseconds of device time since cuda_timer_begin (CUDA events on the backend stream)");
+	m.def("cuda_device_name", []() { return std::string(tfcuda_device_name()); });
+	m.def("cuda_sm_count", []() { return tfcuda_device_sm_count(); });
+	m.def("cuda_device_ptr", [](const PyTensorMemory& t) { RequireCuda("cuda_device_ptr"); return DevPtr(t); });
+
+	m.def("cuda_tensor", [](py::array arr) {
+		RequireCuda("cuda_tensor");
+		py::array c = py::array::ensure(arr, py::array::c_style);
+		py::buffer_info info = c.request();
+		TFDataFormat fmt = FormatOf(info);
+		std::vector<size_t> shape(info.shape.begin(), info.shape.end());
+		TFTensor* t = global_memory_manager->AllocateTensor(shape, fmt);
+		Check(tfcuda_memcpy_h2d(((TFCudaBuffer*)t->buffer)->GetNative(), info.ptr, (size_t)info.size * 4), "cuda_tensor upload");
+		return new PyTensorMemory(t);
+	}, "TensorMemory from a contiguous 4-byte numpy array with one bulk copy", py::return_value_policy::take_ownership);
+
+	m.def("cuda_upload", [](PyTensorMemory& t, py::array arr) {
+		RequireCuda("cuda_upload");
+		py::array c = py::array::ensure(arr, py::array::c_style);
+		py::buffer_info info = c.request();
+		(void)FormatOf(info);
+		if ((size_t)info.size != GetSize(t.tensor_)) throw std::runtime_error("cuda_upload: element count mismatch");
+		Check(tfcuda_memcpy_h2d(DevPtr(t), info.ptr, (size_t)info.size * 4), "cuda_upload");
+	}, "Overwrite an existing TensorMemory from a numpy array of the same size");
+
+	m.def("cuda_numpy", [](const PyTensorMemory& t) -> py::array {
+		RequireCuda("cuda_numpy");
+		std::vector<size_t> shape = t.Shape();
+		py::array out;
+		TFDataFormat f = t.GetFormat();
+		if (f == TFTypeFloat32) out = py::array_t<float>(shape);
+		else if (f == TFTypeInt32) out = py::array_t<int>(shape);
+		else if (f == TFTypeUint32) out = py::array_t<uint>(shape);
+		else throw std::runtime_error("cuda_numpy: bool tensors use .numpy");
+		Check(tfcuda_memcpy_d2h(out.request().ptr, DevPtr(t), GetSize(t.tensor_) * 4), "cuda_numpy");
+		return out;
+	}, "numpy copy of a TensorMemory with one bulk copy");
+
+	// ---- data-parallel exchange -------------------------------------------------------------------
+	m.def("cuda_comm_unique_id", []() {
+		uint8_t id[128];
+		Check(tfcuda_comm_unique_id(id), "cuda_comm_unique_id");
+		return py::bytes(reinterpret_cast<const char*>(id), 128);
+	});
+	m.def("cuda_comm_init", [](py::bytes id, int rank, int world) {
+		RequireCuda("cuda_comm_init");
+		std::string s = id;
+		if (s.size() != 128) throw std::runtime_error("cuda_comm_init: unique id must be 128 bytes");
+		Check(tfcuda_comm_init(reinterpret_cast<const uint8_t*>(s.data()), rank, world), "cuda_comm_init");
+	});
+	m.def("cuda_allreduce", [](PyTensorMemory& t, float scale) {
+		RequireCuda("cuda_allreduce");
+		if (t.GetFormat() != TFTypeFloat32) throw std::runtime_error("cuda_allreduce: float32 tensors only");
+		Check(tfcuda_comm_allreduce_sum_f32(DevPtr(t), GetSize(t.tensor_), scale), "cuda_allreduce");
+	}, py::arg("tensor"), py::arg("scale") = 1.0f, "In-place sum-allreduce over the NCCL communicator, then multiply by scale");
+	m.def("cuda_comm_destroy", []() { tfcuda_comm_destroy(); });
+
+	// ---- library kernels on TensorMemory ------------------------------------------------------------
+	m.def("cuda_radix_sort", [](const PyTensorMemory& keys, py::object values, int max_bits) -> py::object {
+		RequireCuda("cuda_radix_sort");
+		size_t n = GetSize(keys.tensor_);
+		PyTensorMemory* keys_out = NewLike(keys, keys.GetFormat());
+		PyTensorMemory temp({tfcuda_radix_sort_temp_words(n)}, TFTypeUint32);
+		if (values.is_none()) {
+			Check(tfcuda_radix_sort(DevPtr(keys), DevPtr(*keys_out), 0, 0, n, (int)keys.GetFormat().type, max_bits, DevPtr(temp)), "cuda_radix_sort");
+			return py::cast(keys_out, py::return_value_policy::take_ownership);
+		}
+		const PyTensorMemory& vals = values.cast<const PyTensorMemory&>();
+		if (GetSize(vals.tensor_) != n) throw std::runtime_error("cuda_radix_sort: keys and values differ in size");
+		PyTensorMemory* vals_out = NewLike(vals, vals.GetFormat());
+		Check(tfcuda_radix_sort(DevPtr(keys), DevPtr(*keys_out), DevPtr(vals), DevPtr(*vals_out), n, (int)keys.GetFormat().type, max_bits, DevPtr(temp)), "cuda_radix_sort");
+		return py::make_tuple(py::cast(keys_out, py::return_value_policy::take_ownership), py::cast(vals_out, py::return_value_policy::take_ownership));
+	}, py::arg("keys"), py::arg("values") = py::none(), py::arg("max_bits") = 32);
+
+	m.def("cuda_reduce", [](const PyTensorMemory& in, int axis, const std::string& op) {
+		RequireCuda("cuda_reduce");
+		static const std::unordered_map<std::string, int> ops = {{"sum", TFCUDA_RED_SUM}, {"max", TFCUDA_RED_MAX}, {"min", TFCUDA_RED_MIN},
+		    {"mean", TFCUDA_RED_MEAN}, {"norm", TFCUDA_RED_NORM}, {"prod", TFCUDA_RED_PROD}, {"any", TFCUDA_RED_ANY}, {"all", TFCUDA_RED_ALL}};
+		auto it = ops.find(op);
+		if (it == ops.end()) throw std::runtime_error("cuda_reduce: unknown op " + op);
+		std::vector<size_t> shape = in.Shape();
+		int dims = (int)shape.size();
+		if (axis < 0) axis += dims;
+		if (axis < 0 || axis >= dims) throw std::runtime_error("cuda_reduce: axis out of range");
+		size_t outer = 1, inner = 1;
+		for (int i = 0; i < axis; i++) outer *= shape[i];
+		for (int i = axis + 1; i < dims; i++) inner *= shape[i];
+		std::vector<size_t> out_shape;
+		for (int i = 0; i < dims; i++) if (i != axis) out_shape.push_back(shape[i]);
+		if (out_shape.empty()) out_shape.push_back(1);
+		PyTensorMemory* out = new PyTensorMemory(global_memory_manager->AllocateTensor(out_shape, in.GetFormat()));
+		Check(tfcuda_reduce(DevPtr(in), DevPtr(*out), outer, shape[axis], inner, it->second, (int)in.GetFormat().type), "cuda_reduce");
+		return out;
+	}, py::arg("tensor"), py::arg("axis") = -1, py::arg("op") = "sum", py::return_value_policy::take_ownership);
+
+	m.def("cuda_prefix_sum", [](const PyTensorMemory& in, int axis) {
+		RequireCuda("cuda_prefix_sum");
+		std::vector<size_t> shape = in.Shape();
+		int dims = (int)shape.size();
+		if (axis < 0) axis += dims;
+		if (axis < 0 || axis >= dims) throw std::runtime_error("cuda_prefix_sum: axis out of range");
+		size_t outer = 1, inner = 1;
+		for (int i = 0; i < axis; i++) outer *= shape[i];
+		for (int i = axis + 1; i < dims; i++) inner *= shape[i];
+		PyTensorMemory* out = NewLike(in, in.GetFormat());
+		Check(tfcuda_prefix_sum(DevPtr(in), DevPtr(*out), outer, shape[axis], inner, (int)in.GetFormat().type), "cuda_prefix_sum");
+		return out;
+	}, py::arg("tensor"), py::arg("axis") = -1, py::return_value_policy::take_ownership);
+
+	m.def("cuda_matmul", [](const PyTensorMemory& a, const PyTensorMemory& b, int mode) {
+		RequireCuda("cuda_matmul");
+		std::vector<size_t> sa = a.Shape(), sb = b.Shape();
+		if (sa.size() < 2 || sb.size() != 2) throw std::runtime_error("cuda_matmul: expects A[..., M, K] @ B[K, N]");
+		size_t k = sa.back(), mm = 1;
+		for (size_t i = 0; i + 1 < sa.size(); i++) mm *= sa[i];
+		if (sb[0] != k) throw std::runtime_error("cuda_matmul: inner dimensions differ");
+		std::vector<size_t> so(sa.begin(), sa.end() - 1);
+		so.push_back(sb[1]);
+		PyTensorMemory* c = new PyTensorMemory(global_memory_manager->AllocateTensor(so, TFTypeFloat32));
+		Check(tfcuda_matmul(DevPtr(a), DevPtr(b), DevPtr(*c), 1, mm, sb[1], k, mode), "cuda_matmul");
+		return c;
+	}, py::arg("a"), py::arg("b"), py::arg("mode") = 0, py::return_value_policy::take_ownership);
+
+	m.def("cuda_scatter_add", [](PyTensorMemory& dst, const PyTensorMemory& index, const PyTensorMemory& src) {
+		RequireCuda("cuda_scatter_add");
+		size_t n = GetSize(src.tensor_);
+		if (GetSize(index.tensor_) != n) throw std::runtime_error("cuda_scatter_add: index and src differ in size");
+		Check(tfcuda_scatter_add(DevPtr(dst), DevPtr(index), DevPtr(src), n, GetSize(dst.tensor_), (int)dst.GetFormat().type), "cuda_scatter_add");
+	});
+
+	m.def("cuda_nbody_step", [](const PyTensorMemory& x, const PyTensorMemory& v, float dt, float eps) {
+		RequireCuda("cuda_nbody_step");
+		std::vector<size_t> s = x.Shape();
+		if (s.size() != 2 || s[1] != 3) throw std::runtime_error("cuda_nbody_step: X must be [N,3]");
+		PyTensorMemory* xn = NewLike(x, TFTypeFloat32);
+		PyTensorMemory* vn = NewLike(v, TFTypeFloat32);
+		Check(tfcuda_nbody_step(DevPtr(x), DevPtr(v), DevPtr(*xn), DevPtr(*vn), s[0], dt, eps), "cuda_nbody_step");
+		return py::make_tuple(py::cast(xn, py::return_value_policy::take_ownership), py::cast(vn, py::return_value_policy::take_ownership));
+	}, py::arg("x"), py::arg("v"), py::arg("dt") = 0.001f, py::arg("eps") = 1e-4f);
+}
+
+}  // namespace TensorFrost

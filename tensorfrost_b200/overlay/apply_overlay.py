@@ -1,0 +1,128 @@
+#!/usr/bin/env python3
+"""Turn a scratch copy of the reference tree into the CUDA-enabled TensorFrost module.
+
+The reference has no backend registry: backends and kernel languages are enums plus `switch`
+statements (Backend/Backend.h:22-35, Backend/Backend.cpp:49-68,78-89, CodeGen/Generators.cpp:10-22)
+and the pybind module binds both enums by value (Frontend/Python/PybindModule.cpp:52-58,76-83).
+Adding a backend therefore means adding enum values and switch cases.  This script performs exactly
+those insertions on a COPY of the reference (never on /root/reference, never stored in git) and drops
+our own sources (this directory) next to them.  Every edit is anchored on a short literal of the
+reference and fails loudly if the anchor is missing, so a reference update cannot silently
+produce a half-patched tree.  INTEGRATION.md shows the same edits as the patch a maintainer would apply.
+
+usage: apply_overlay.py <scratch_reference_root> <repo_root>
+"""
+import shutil
+import sys
+from pathlib import Path
+
+
+class Patch:
+    def __init__(self, path: Path):
+        self.path = path
+        self.text = path.read_text()
+
+    def insert_after(self, anchor: str, addition: str, occurrence: int = 0):
+        idx = self._find(anchor, occurrence) + len(anchor)
+        self.text = self.text[:idx] + addition + self.text[idx:]
+
+    def insert_before(self, anchor: str, addition: str, occurrence: int = 0):
+        idx = self._find(anchor, occurrence)
+        self.text = self.text[:idx] + addition + self.text[idx:]
+
+    def replace(self, anchor: str, new: str, occurrence: int = 0):
+        idx = self._find(anchor, occurrence)
+        self.text = self.text[:idx] + new + self.text[idx + len(anchor):]
+
+    def _find(self, anchor: str, occurrence: int) -> int:
+        idx = -1
+        for _ in range(occurrence + 1):
+            idx = self.text.find(anchor, idx + 1)
+            if idx < 0:
+                raise SystemExit(f"apply_overlay: anchor {anchor!r} (occurrence {occurrence}) not found in {self.path}")
+        return idx
+
+    def save(self):
+        self.path.write_text(self.text)
+
+
+def main():
+    ref = Path(sys.argv[1])
+    repo = Path(sys.argv[2])
+    tf = ref / "TensorFrost"
+    overlay = repo / "tensorfrost_b200" / "overlay"
+
+    # 1. our sources: backend glue + emitter (TensorFrost/CMakeLists.txt globs *.cpp recursively)
+    for rel in ["Backend/Backends/CUDA/CUDA.h", "Backend/Backends/CUDA/CudaBackend.cpp",
+                "Backend/Backends/CUDA/CudaPython.cpp", "Backend/CodeGen/Langs/CUDA.cpp"]:
+        dst = tf / rel
+        dst.parent.mkdir(parents=True, exist_ok=True)
+        shutil.copyfile(overlay / rel, dst)
+
+    # 2. enums + include (Backend/Backend.h)
+    p = Patch(tf / "Backend" / "Backend.h")
+    p.insert_after('#include "Backends/OpenGL/OpenGL.h"\n', '#include "Backends/CUDA/CUDA.h"\n')
+    p.insert_after("\tOpenGL,\n", "\tCUDA,\n")           # enum class BackendType
+    p.insert_after("\tGLSL,\n", "\tCUDA,\n")             # enum class CodeGenLang
+    p.save()
+
+    # 3. backend switch, kernel compilation, regions (Backend/Backend.cpp)
+    p = Patch(tf / "Backend" / "Backend.cpp")
+    p.insert_after("\t\t\t\tStopOpenGL();\n\t\t\t\tbreak;\n",
+                   "\t\t\tcase BackendType::CUDA:\n\t\t\t\tStopCUDA();\n\t\t\t\tbreak;\n")
+    p.insert_before("\t\tcase BackendType::OpenGL:\n\t\t\tStartOpenGL();",
+                    "\t\tcase BackendType::CUDA:\n"
+                    "\t\t\tStartCUDA();\n"
+                    "\t\t\tcurrent_kernel_lang = CodeGenLang::CUDA;\n"
+                    "\t\t\tcudaKernelCompileOptions = compilerOptions;  // NVRTC flags; the host program needs none\n"
+                    "\t\t\tkernelCompileOptions = \"-O1\";\n"
+                    "\t\t\tglobal_memory_manager = new CudaMemoryManager();\n"
+                    "\t\t\tglobal_kernel_manager = new CudaKernelManager();\n"
+                    "\t\t\tbreak;\n")
+    p.insert_after("auto start_time = chrono::high_resolution_clock::now();\n",
+                   "\tif (current_backend == BackendType::CUDA) {\n"
+                   "\t\t((CudaKernelManager*)global_kernel_manager)->CompileProgram(program);\n"
+                   "\t}\n")
+    p.insert_after("\t\t\tcase BackendType::CPU:\n\t\t\t\t//already in the host program\n\t\t\t\tbreak;\n",
+                   "\t\t\tcase BackendType::CUDA:\n\t\t\t\t//compiled above, all kernels of the program at once\n\t\t\t\tbreak;\n")
+    p.insert_before("\tif (current_backend == BackendType::OpenGL) {\n\t\tif (begin) {",
+                    "\tif (current_backend == BackendType::CUDA) {\n\t\tCudaRegion(name, begin);\n\t}\n")
+    p.save()
+
+    # 4. emitter dispatch (Backend/CodeGen/Generators.{h,cpp})
+    p = Patch(tf / "Backend" / "CodeGen" / "Generators.cpp")
+    p.insert_before("\t\tdefault:\n\t\t\tthrow std::runtime_error(\"Code generation for this language",
+                    "\t\tcase CodeGenLang::CUDA:\n\t\t\tGenerateCUDAKernel(program, kernel);\n\t\t\treturn;\n")
+    p.save()
+    p = Patch(tf / "Backend" / "CodeGen" / "Generators.h")
+    p.insert_after("void GenerateGLSLKernel(Program* program, Kernel* kernel);\n",
+                   "void GenerateCUDAKernel(Program* program, Kernel* kernel);\n")
+    p.save()
+
+    # 5. python bindings (Frontend/Python/PybindModule.cpp)
+    p = Patch(tf / "Frontend" / "Python" / "PybindModule.cpp")
+    p.insert_after("void ModuleDefinitions(py::module& m);\n", "void CudaDefinitions(py::module& m);\n")
+    p.insert_after('backend_type.value("opengl", BackendType::OpenGL);\n', '\tbackend_type.value("cuda", BackendType::CUDA);\n')
+    p.insert_after('code_gen_lang.value("hlsl", CodeGenLang::HLSL);\n', '\tcode_gen_lang.value("cuda", CodeGenLang::CUDA);\n')
+    p.insert_after('m.attr("opengl") = BackendType::OpenGL;\n', '\tm.attr("cuda") = BackendType::CUDA;\n')
+    p.insert_after('m.attr("hlsl_lang") = CodeGenLang::HLSL;\n', '\tm.attr("cuda_lang") = CodeGenLang::CUDA;\n')
+    p.insert_after("\tModuleDefinitions(m);\n", "\tCudaDefinitions(m);\n")
+    p.save()
+
+    # 6. build: link libtfcuda.so (found next to the module at run time) and see include/tfcuda.h
+    p = Patch(tf / "CMakeLists.txt")
+    p.text += (
+        "\n# --- tensorfrost_b200 overlay ---\n"
+        f"target_include_directories(TensorFrost PRIVATE {repo / 'include'})\n"
+        f"target_link_libraries(TensorFrost PRIVATE {repo / 'tensorfrost_b200' / 'lib' / 'libtfcuda.so'})\n"
+        "set_target_properties(TensorFrost PROPERTIES BUILD_WITH_INSTALL_RPATH ON INSTALL_RPATH \"$ORIGIN\")\n"
+    )
+    # glad's generator otherwise downloads gl.xml; REPRODUCIBLE uses the vendored spec
+    p.replace("glad_gl_core_46 SHARED API", "glad_gl_core_46 STATIC REPRODUCIBLE API")
+    p.save()
+
+    print("apply_overlay: patched", ref)
+
+
+if __name__ == "__main__":
+    main()
