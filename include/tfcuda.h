@@ -179,6 +179,25 @@ uint64_t tfcuda_launch_count(void);
 int tfcuda_timer_begin(void);
 int tfcuda_timer_end(float* ms);
 
+/* Per-kernel profiling.  While enabled every launch (emitted or library) is bracketed by a CUDA-event pair on the
+ * runtime stream; records aggregate per kernel name.  `bytes` is the ALGORITHMIC traffic the caller attributes to the
+ * launches (tfcuda_profile_add_bytes; the in-tree glue adds the size of every tensor bound to a dispatch, each once —
+ * SURVEY.md §8d).  Used by bench.py for the roofline of the dominant kernel; off by default (no overhead). */
+typedef struct TFCudaProfileRecord {
+	char name[64];
+	uint64_t launches;
+	double total_ms;
+	double bytes;
+} TFCudaProfileRecord;
+int tfcuda_profile_enable(int on);
+int tfcuda_profile_reset(void);
+int tfcuda_profile_add_bytes(size_t kernel_id, double bytes);
+size_t tfcuda_profile_records(TFCudaProfileRecord* out, size_t capacity); /* syncs; returns the number of records */
+
+/* Page-locked host memory for host<->device copies that run at full PCIe rate (bench.py's e2e leg). */
+void* tfcuda_host_alloc(size_t bytes);
+int tfcuda_host_free(void* p);
+
 /* ------------------------------------------------------------------------------------------
  * Library kernels (hand-written sm_100a).  They replace the generic lowering of
  * Compiler/Implementations.cpp (ComputeReduction :243-303, ComputeScan :305-359, ComputeMatMul

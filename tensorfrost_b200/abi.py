@@ -38,6 +38,10 @@ class TFCudaKernelSource(C.Structure):
                 ("n_var", C.c_uint), ("library_op", C.c_uint)]
 
 
+class TFCudaProfileRecord(C.Structure):
+    _fields_ = [("name", C.c_char * 64), ("launches", u64), ("total_ms", C.c_double), ("bytes", C.c_double)]
+
+
 # name -> (restype, argtypes)
 EXPORTS = {
     "tfcuda_init": (i32, [i32]),
@@ -70,6 +74,12 @@ EXPORTS = {
     "tfcuda_launch_count": (u64, []),
     "tfcuda_timer_begin": (i32, []),
     "tfcuda_timer_end": (i32, [C.POINTER(f32)]),
+    "tfcuda_profile_enable": (i32, [i32]),
+    "tfcuda_profile_reset": (i32, []),
+    "tfcuda_profile_add_bytes": (i32, [sz, C.c_double]),
+    "tfcuda_profile_records": (sz, [C.POINTER(TFCudaProfileRecord), sz]),
+    "tfcuda_host_alloc": (C.c_void_p, [sz]),
+    "tfcuda_host_free": (i32, [C.c_void_p]),
     "tfcuda_reduce": (i32, [u64, u64, sz, sz, sz, i32, i32]),
     "tfcuda_prefix_sum": (i32, [u64, u64, sz, sz, sz, i32]),
     "tfcuda_radix_sort_temp_words": (sz, [sz]),

@@ -95,6 +95,7 @@ extern "C" int tfcuda_matmul(uint64_t a, uint64_t b, uint64_t c, size_t batch, s
 	float* pc = reinterpret_cast<float*>(c);
 	if (mode == 0 || mode == 1) return tfcuda_matmul_tcgen05(pa, pb, pc, batch, m, n, k, mode);
 	if (mode != 2) { tfcuda::set_error("tfcuda_matmul: unknown mode"); return 1; }
+	tfcuda::ProfileScope prof("lib/matmul_ffma");
 	dim3 grid((unsigned)((n + BN - 1) / BN), (unsigned)((m + BM - 1) / BM), (unsigned)batch);
 	matmul_ffma_kernel<<<grid, MM_THREADS, 0, s.stream>>>(pa, pb, pc, (int)m, (int)n, (int)k);
 	return tfcuda::check_launch("tfcuda_matmul(ffma)");

@@ -72,6 +72,7 @@ extern "C" int tfcuda_nbody_step(uint64_t x, uint64_t v, uint64_t x_new, uint64_
 	if (!s.initialized) { tfcuda::set_error("tfcuda_nbody_step: not initialised"); return 1; }
 	if (n == 0) return 0;
 	if (n > 0x2fffffffull) { tfcuda::set_error("tfcuda_nbody_step: too many bodies"); return 1; }
+	tfcuda::ProfileScope prof("lib/nbody");
 	unsigned blocks = (unsigned)((n + NB_THREADS * NB_PER_THREAD - 1) / (NB_THREADS * NB_PER_THREAD));
 	nbody_kernel<<<blocks, NB_THREADS, 0, s.stream>>>(reinterpret_cast<const float*>(x), reinterpret_cast<const float*>(v), reinterpret_cast<float*>(x_new),
 	                                                  reinterpret_cast<float*>(v_new), (int)n, dt, eps);

@@ -284,8 +284,11 @@ extern "C" int tfcuda_radix_sort(uint64_t keys_in, uint64_t keys_out, uint64_t v
 
 	const unsigned* kin = reinterpret_cast<const unsigned*>(keys_in);
 	unsigned hist_blocks = (unsigned)std::min<size_t>((n / 4 + 511) / 512 + 1, (size_t)s.sm_count * 4);
-	digit_histogram_kernel<<<hist_blocks, 512, 0, s.stream>>>(kin, n, mode, passes, max_bits, hist);
-	if (tfcuda::check_launch("digit_histogram_kernel")) return 1;
+	{
+		tfcuda::ProfileScope prof("lib/radix_histogram", 4.0 * n);
+		digit_histogram_kernel<<<hist_blocks, 512, 0, s.stream>>>(kin, n, mode, passes, max_bits, hist);
+		if (tfcuda::check_launch("digit_histogram_kernel")) return 1;
+	}
 	scan_histogram_kernel<<<passes, RS_BINS, 0, s.stream>>>(hist);
 	if (tfcuda::check_launch("scan_histogram_kernel")) return 1;
 
@@ -307,6 +310,7 @@ extern "C" int tfcuda_radix_sort(uint64_t keys_in, uint64_t keys_out, uint64_t v
 		a.digit_base = hist + p * RS_BINS;
 		a.desc = desc + (size_t)p * tiles * RS_BINS;
 		a.ticket = tickets + p;
+		tfcuda::ProfileScope prof("lib/radix_onesweep", (has_values ? 16.0 : 8.0) * n);
 		if (has_values) onesweep_kernel<true><<<(unsigned)tiles, RS_THREADS, smem_bytes(true), s.stream>>>(a);
 		else onesweep_kernel<false><<<(unsigned)tiles, RS_THREADS, smem_bytes(false), s.stream>>>(a);
 		if (tfcuda::check_launch("onesweep_kernel")) return 1;

@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(256) reduce_mid_kernel(const T* __restrict__ i
 template <typename T, int OP>
 int launch(const void* in, void* out, size_t outer, size_t n, size_t inner) {
 	tfcuda::State& s = tfcuda::state();
+	tfcuda::ProfileScope prof("lib/reduce");
 	const T* pin = static_cast<const T*>(in);
 	T* pout = static_cast<T*>(out);
 	size_t max_blocks = (size_t)s.sm_count * 16;

@@ -269,6 +269,62 @@ static void compile_chunk(Chunk& c, const std::vector<std::string>& opts, bool u
 	if (c.ok && use_cache) write_file_atomic(path, c.cubin);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Profiling
+// ------------------------------------------------------------------------------------------------
+struct ProfileSample { cudaEvent_t a, b; };
+struct ProfileEntry {
+	std::vector<ProfileSample> pending;
+	uint64_t launches = 0;
+	double total_ms = 0.0;
+	double bytes = 0.0;
+};
+static bool g_profile_on = false;
+static std::unordered_map<std::string, ProfileEntry> g_profile;
+static std::vector<cudaEvent_t> g_event_pool;
+
+static cudaEvent_t take_event() {
+	if (!g_event_pool.empty()) {
+		cudaEvent_t e = g_event_pool.back();
+		g_event_pool.pop_back();
+		return e;
+	}
+	cudaEvent_t e;
+	cudaEventCreate(&e);
+	return e;
+}
+
+void profile_begin(const char* name) {
+	if (!g_profile_on) return;
+	ProfileEntry& pe = g_profile[name];
+	ProfileSample smp{take_event(), take_event()};
+	cudaEventRecord(smp.a, g_state.stream);
+	pe.pending.push_back(smp);
+}
+
+void profile_end(const char* name, double bytes) {
+	if (!g_profile_on) return;
+	ProfileEntry& pe = g_profile[name];
+	if (pe.pending.empty()) return;
+	cudaEventRecord(pe.pending.back().b, g_state.stream);
+	pe.launches++;
+	pe.bytes += bytes;
+}
+
+static void profile_resolve() {
+	cudaStreamSynchronize(g_state.stream);
+	for (auto& kv : g_profile) {
+		for (ProfileSample& smp : kv.second.pending) {
+			float ms = 0;
+			if (cudaEventElapsedTime(&ms, smp.a, smp.b) == cudaSuccess) kv.second.total_ms += ms;
+			g_event_pool.push_back(smp.a);
+			g_event_pool.push_back(smp.b);
+		}
+		kv.second.pending.clear();
+	}
+	(void)cudaGetLastError();
+}
+
 static std::string drv_err(CUresult r) {
 	const char* s = nullptr;
 	if (g_state.drv.GetErrorString) g_state.drv.GetErrorString(r, &s);
@@ -605,6 +661,7 @@ int tfcuda_launch(size_t kernel_id, const uint64_t* mem, size_t n_mem, const uin
 	// grid.x is limited to 2^31-1: larger dispatches are split with the _kernel_block_offset word
 	const size_t kMaxGrid = 0x7fffffffull;
 	size_t done = 0;
+	ProfileScope prof(e.entry.c_str());
 	while (done < work_group_count) {
 		size_t now = std::min(kMaxGrid, work_group_count - done);
 		if (offset_word) *offset_word = vars[n_var - 1] + (uint32_t)done;
@@ -627,10 +684,71 @@ int tfcuda_dispatch(const TFDispatchInfo* info) {
 	if (n > 256) { set_error("tfcuda_dispatch: too many buffers"); return 1; }
 	for (size_t i = 0; i < info->read_write_count; i++) ptrs[i] = dptr_of(info->read_write_tensors[i].buffer);
 	for (size_t i = 0; i < info->read_only_count; i++) ptrs[info->read_write_count + i] = dptr_of(info->read_only_tensors[i].buffer);
+	if (g_profile_on) {
+		double bytes = 0;
+		for (size_t i = 0; i < info->read_write_count; i++) {
+			size_t words = 1;
+			for (size_t d = 0; d < info->read_write_tensors[i].dim; d++) words *= info->read_write_tensors[i].shape[d];
+			bytes += 4.0 * words;
+		}
+		tfcuda_profile_add_bytes(info->kernel_id, bytes);
+	}
 	return tfcuda_launch(info->kernel_id, ptrs, n, info->variables, info->variable_count, info->work_group_count);
 }
 
 uint64_t tfcuda_launch_count(void) { return g_state.launches; }
+
+int tfcuda_profile_enable(int on) {
+	if (!g_state.initialized) { set_error("tfcuda: not initialised"); return 1; }
+	if (!on && g_profile_on) profile_resolve();
+	g_profile_on = on != 0;
+	return 0;
+}
+
+int tfcuda_profile_reset(void) {
+	if (g_state.initialized) profile_resolve();
+	g_profile.clear();
+	return 0;
+}
+
+int tfcuda_profile_add_bytes(size_t kernel_id, double bytes) {
+	if (!g_profile_on) return 0;
+	if (kernel_id >= g_kernels.size()) { set_error("tfcuda_profile_add_bytes: unknown kernel"); return 1; }
+	g_profile[g_kernels[kernel_id].entry].bytes += bytes;
+	return 0;
+}
+
+size_t tfcuda_profile_records(TFCudaProfileRecord* out, size_t capacity) {
+	if (g_state.initialized) profile_resolve();
+	size_t i = 0;
+	for (auto& kv : g_profile) {
+		if (out && i < capacity) {
+			memset(&out[i], 0, sizeof(out[i]));
+			strncpy(out[i].name, kv.first.c_str(), sizeof(out[i].name) - 1);
+			out[i].launches = kv.second.launches;
+			out[i].total_ms = kv.second.total_ms;
+			out[i].bytes = kv.second.bytes;
+		}
+		i++;
+	}
+	return i;
+}
+
+void* tfcuda_host_alloc(size_t bytes) {
+	void* p = nullptr;
+	cudaError_t e = cudaMallocHost(&p, bytes ? bytes : 1);
+	if (e != cudaSuccess) {
+		set_error("tfcuda_host_alloc: " + cuda_err(e));
+		(void)cudaGetLastError();
+		return nullptr;
+	}
+	return p;
+}
+
+int tfcuda_host_free(void* p) {
+	if (p) TFCUDA_CHECK(cudaFreeHost(p));
+	return 0;
+}
 
 int tfcuda_timer_begin(void) {
 	if (!g_state.initialized) { set_error("tfcuda: not initialised"); return 1; }

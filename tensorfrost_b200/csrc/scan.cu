@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(256) scan_mid_kernel(const T* __restrict__ in,
 template <typename T>
 int launch(uint64_t in, uint64_t out, size_t outer, size_t n, size_t inner) {
 	tfcuda::State& s = tfcuda::state();
+	tfcuda::ProfileScope prof("lib/prefix_sum");
 	const T* pin = reinterpret_cast<const T*>(in);
 	T* pout = reinterpret_cast<T*>(out);
 	if (inner == 1) {

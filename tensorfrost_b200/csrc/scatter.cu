@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(256) scatter_add_kernel(T* __restrict__ dst, c
 template <typename T>
 int launch(uint64_t dst, uint64_t index, uint64_t src, size_t n, size_t dst_words) {
 	tfcuda::State& s = tfcuda::state();
+	tfcuda::ProfileScope prof("lib/scatter_add");
 	unsigned blocks = (unsigned)std::min((n + 255) / 256, (size_t)s.sm_count * 16);
 	scatter_add_kernel<T><<<blocks ? blocks : 1, 256, 0, s.stream>>>(reinterpret_cast<T*>(dst), reinterpret_cast<const int*>(index),
 	                                                                   reinterpret_cast<const T*>(src), n, (int)dst_words - 1);

@@ -71,6 +71,17 @@ void require_init();  // throws std::runtime_error when tfcuda_init has not succ
 		}                                                                                    \
 	} while (0)
 
+// Profiling hooks (runtime.cu): a ProfileScope brackets the launches of one named kernel with an event pair when
+// profiling is enabled, and is free otherwise.
+void profile_begin(const char* name);
+void profile_end(const char* name, double bytes);
+struct ProfileScope {
+	const char* name;
+	double bytes;
+	ProfileScope(const char* n, double b = 0.0) : name(n), bytes(b) { profile_begin(name); }
+	~ProfileScope() { profile_end(name, bytes); }
+};
+
 // library kernels report launch errors through this
 inline int check_launch(const char* what) {
 	cudaError_t e = cudaGetLastError();

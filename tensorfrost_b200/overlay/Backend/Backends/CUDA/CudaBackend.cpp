@@ -82,6 +82,10 @@ void CudaKernelManager::DispatchKernel(TFDispatchInfo info) {
 	for (size_t i = 0; i < info.read_write_count; i++) {
 		ptrs[i] = ((TFCudaBuffer*)info.read_write_tensors[i].buffer)->GetNative();
 	}
+	// algorithmic traffic of this dispatch = every bound tensor once (only accounted while profiling)
+	double bytes = 0;
+	for (size_t i = 0; i < info.read_write_count; i++) bytes += 4.0 * (double)GetSize(&info.read_write_tensors[i]);
+	tfcuda_profile_add_bytes(info.kernel_id, bytes);
 	if (tfcuda_launch(info.kernel_id, ptrs, info.read_write_count, info.variables, info.variable_count, info.work_group_count) != 0) {
 		Fail("dispatch of kernel " + std::to_string(info.kernel_id) + " failed");
 	}

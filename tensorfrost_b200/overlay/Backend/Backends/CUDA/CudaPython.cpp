@@ -68,6 +68,37 @@ void CudaDefinitions(py::module& m) {
 	m.def("cuda_sm_count", []() { return tfcuda_device_sm_count(); });
 	m.def("cuda_device_ptr", [](const PyTensorMemory& t) { RequireCuda("cuda_device_ptr"); return DevPtr(t); });
 
+	m.def("cuda_profile_enable", [](bool on) { Check(tfcuda_profile_enable(on ? 1 : 0), "cuda_profile_enable"); }, py::arg("on") = true,
+	      "Bracket every kernel launch with CUDA events and accumulate per-kernel time / algorithmic bytes");
+	m.def("cuda_profile_reset", []() { tfcuda_profile_reset(); });
+	m.def("cuda_profile_records", []() {
+		size_t n = tfcuda_profile_records(nullptr, 0);
+		std::vector<TFCudaProfileRecord> recs(n);
+		n = tfcuda_profile_records(recs.data(), recs.size());
+		py::list out;
+		for (size_t i = 0; i < n && i < recs.size(); i++) {
+			py::dict d;
+			d["name"] = std::string(recs[i].name);
+			d["launches"] = recs[i].launches;
+			d["total_ms"] = recs[i].total_ms;
+			d["bytes"] = recs[i].bytes;
+			out.append(d);
+		}
+		return out;
+	}, "Per-kernel profile records: name, launches, total_ms (CUDA events), bytes (tensors bound, each once)");
+
+	m.def("cuda_pinned_array", [](std::vector<size_t> shape, const std::string& dtype) -> py::array {
+		size_t count = 1;
+		for (size_t d : shape) count *= d;
+		void* p = tfcuda_host_alloc(count * 4);
+		if (!p) throw std::runtime_error(std::string("cuda_pinned_array: ") + tfcuda_last_error());
+		py::capsule owner(p, [](void* q) { tfcuda_host_free(q); });
+		if (dtype == "float32") return py::array_t<float>(shape, static_cast<float*>(p), owner);
+		if (dtype == "int32") return py::array_t<int>(shape, static_cast<int*>(p), owner);
+		if (dtype == "uint32") return py::array_t<uint>(shape, static_cast<uint*>(p), owner);
+		throw std::runtime_error("cuda_pinned_array: dtype must be float32, int32 or uint32");
+	}, py::arg("shape"), py::arg("dtype") = "float32", "numpy array backed by page-locked host memory (full-rate host<->device copies)");
+
 	m.def("cuda_tensor", [](py::array arr) {
 		RequireCuda("cuda_tensor");
 		py::array c = py::array::ensure(arr, py::array::c_style);

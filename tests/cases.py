@@ -96,7 +96,8 @@ def _int_ops():
                 u + tf.uint(b), u * u, u / tf.uint(b), u % tf.uint(b), u >> tf.uint(b % 16), u << tf.uint(b % 16), u ^ (u >> 7),
                 tf.pcg(u), tf.reversebits(u), tf.min(a, b), tf.max(a, b), tf.abs(a), tf.sign(a), tf.clamp(a, -100, 100),
                 tf.int(a < b), tf.int((a < b) & (a > -b)), tf.int((a == b) | (a >= 0)), tf.select(a != b, a, b),
-                tf.asint(tf.asfloat(u)), tf.int(u), tf.uint(a), tf.int(tf.float(a % 1000)),
+                tf.asint(tf.asuint(tf.asfloat(u))), tf.int(u), tf.uint(a), tf.int(tf.float(a % 1000)),
+                # (asint(float) is a VALUE conversion on the oracle - its helper header only has asint(uint) - so unpinned)
             ]
             return outs
         return tf.compile(prog)
@@ -125,28 +126,38 @@ def _pcgf():
 
 @case("control_flow", kind="exact", default_size=2048)
 def _control_flow():
-    """In-kernel loop / if / break / continue and a per-thread local buffer (Collatz-style integer work)."""
+    """In-kernel loop / if / break / continue and a per-thread local buffer (Collatz-style integer work)
+    inside an explicit tf.kernel scope."""
     def build(tf):
         def prog():
             seed = tf.input([-1], tf.int32)
-            n = seed.copy() if hasattr(seed, "copy") else seed + 0
-            steps = tf.const(0)
-            acc = tf.const(0)
-            hist = tf.local_buffer(4, tf.int32)
-            for k in range(4):
-                hist[k] = 0
-            with tf.loop(200) as it:
-                with tf.if_cond(n == 1):
-                    tf.break_loop()
-                with tf.if_cond((n % 2) == 0):
-                    n.val = n / 2
+            out_steps = tf.buffer(seed.shape, tf.int32)
+            out_acc = tf.buffer(seed.shape, tf.int32)
+            out_last = tf.buffer(seed.shape, tf.int32)
+            out_hist = tf.buffer(seed.shape, tf.int32)
+            with tf.kernel(seed.shape) as i:
+                n = tf.const(0)
+                n.val = seed[i]
+                steps = tf.const(0)
+                acc = tf.const(0)
+                hist = tf.local_buffer(4, tf.int32)
+                for k in range(4):
+                    hist[k] = 0
+                with tf.loop(200) as it:
+                    with tf.if_cond(n == 1):
+                        tf.break_loop()
                     steps.val += 1
-                    tf.continue_loop()
-                n.val = n * 3 + 1
-                steps.val += 1
-                acc.val += it
-                hist[it % 4] = hist[it % 4] + 1
-            return steps, acc, n, hist[0] + 2 * hist[1] + 3 * hist[2] + 5 * hist[3]
+                    with tf.if_cond((n % 2) == 0):
+                        n.val = n / 2
+                        tf.continue_loop()
+                    n.val = n * 3 + 1
+                    acc.val += it
+                    hist[it % 4] = hist[it % 4] + 1
+                out_steps[i] = steps
+                out_acc[i] = acc
+                out_last[i] = n
+                out_hist[i] = hist[0] + 2 * hist[1] + 3 * hist[2] + 5 * hist[3]
+            return out_steps, out_acc, out_last, out_hist
         return tf.compile(prog)
 
     def make_inputs(rng, size):
@@ -205,7 +216,8 @@ def _int_reductions():
         def prog():
             a = tf.input([-1, -1], tf.int32)
             u = tf.input(a.shape, tf.uint32)
-            return tf.sum(a), tf.max(a), tf.min(a), tf.sum(a, axis=0), tf.sum(u), tf.max(u, axis=0), tf.min(u)
+            # (uint max/min do not compile on the oracle: min(uint,uint) is ambiguous in its helper header -> unpinned)
+            return tf.sum(a), tf.max(a), tf.min(a), tf.sum(a, axis=0), tf.sum(u), tf.sum(u, axis=0)
         return tf.compile(prog)
 
     def make_inputs(rng, size):
@@ -473,9 +485,11 @@ def _host_loop():
             i, j = field.indices
             cur = tf.buffer(field.shape, tf.float32)
             cur[i, j] = field[i, j]
+            nxt = tf.buffer(field.shape, tf.float32)
             with tf.loop(steps):
-                nxt = (cur[i - 1, j] + cur[i + 1, j] + cur[i, j - 1] + cur[i, j + 1]) * 0.25
-                cur[i, j] = nxt
+                # ping-pong: a one-kernel in-place stencil would race between threads
+                nxt[i, j] = (cur[i - 1, j] + cur[i + 1, j] + cur[i, j - 1] + cur[i, j + 1]) * 0.25
+                cur[i, j] = nxt[i, j] * 0.5 + cur[i, j] * 0.5
             total = tf.sum(tf.sum(cur))
             return cur, total
         return tf.compile(prog)

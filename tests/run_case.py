@@ -5,7 +5,9 @@ from oracle/_ref) and the CUDA backend never share a process: parity tests run t
 and compare the .npz files.
 
 usage: python tests/run_case.py <cpu|cpu_fast|cuda> <out.npz> <case[:size[:seed]]> [...]
-  cpu       oracle, compiled with "-O3 -fopenmp" (no fast-math): the parity reference
+  cpu       oracle, compiled with "-O3 -fopenmp -include math.h" (no fast-math): the parity reference.
+            `-include math.h` gives the generated C++ the float overload of abs() that the reference's author gets from
+            MSVC's <cmath>; with g++ the generated `abs(x)` on a float otherwise binds to ::abs(int) and truncates.
   cpu_fast  oracle with the reference's default flags (-O3 -ffast-math -fopenmp): timing only
   cuda      the B200 backend
 """
@@ -21,6 +23,9 @@ sys.path.insert(0, HERE)
 sys.path.insert(0, ROOT)
 
 
+ORACLE_PARITY_FLAGS = "-O3 -fopenmp -include math.h"
+
+
 def load_backend(which):
     if which in ("cpu", "cpu_fast"):
         ref = os.path.join(ROOT, "oracle", "_ref")
@@ -28,7 +33,7 @@ def load_backend(which):
             raise SystemExit("oracle/_ref not built (run oracle/build_ref.sh where /root/reference exists)")
         sys.path.insert(0, ref)
         import TensorFrost as tf
-        tf.initialize(tf.cpu, "-O3 -fopenmp" if which == "cpu" else "")
+        tf.initialize(tf.cpu, ORACLE_PARITY_FLAGS if which == "cpu" else "")
         return tf
     if which == "cuda":
         import tensorfrost_b200

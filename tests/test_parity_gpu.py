@@ -1,0 +1,74 @@
+"""GPU parity: every case of tests/cases.py on the CUDA backend vs the reference's own C++/OpenMP backend.
+
+Two pins:
+  * the committed golden fixtures (tests/golden/*.npz) — outputs of the reference, generated in the build container;
+  * a LIVE run of the reference (oracle/_ref travels to the GPU box as a built .so) in a separate process, at a
+    different seed and size than the fixture, when oracle/_ref is present.
+Bars: bit-exact for integer / index / sort / scan / atomic work; relative tolerance written per case for fp32.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import cases
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLDEN = os.path.join(HERE, "golden")
+HAVE_ORACLE = os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "TensorFrost"))
+
+pytestmark = pytest.mark.gpu
+
+_programs = {}
+
+
+def _run_cuda(tf, name, seed, size):
+    outs, prog = cases.run_case(tf, name, seed=seed, size=size, program=_programs.get(name))
+    _programs[name] = prog
+    return outs
+
+
+@pytest.mark.parametrize("name", sorted(cases.CASES))
+def test_case_matches_golden(tf_cuda, name):
+    path = os.path.join(GOLDEN, f"{name}.npz")
+    assert os.path.exists(path), f"no golden fixture for {name}; run tests/golden/make_golden.py"
+    g = np.load(path)
+    want = []
+    while f"out{len(want)}" in g:
+        want.append(g[f"out{len(want)}"])
+    got = _run_cuda(tf_cuda, name, int(g["seed"]), int(g["size"]))
+    cases.compare(cases.CASES[name], got, want)
+
+
+# a second size/seed per case, checked against a live oracle process
+LIVE = {
+    "wave": 301, "math_ops": 5000, "int_ops": 5000, "control_flow": 3000, "reshape_reduce": 23, "row_reductions": 4096,
+    "int_reductions": 257, "prefix_sum": 10000, "split_merge": 96, "sort_radix_u32": 100003, "sort_radix_f32": 65536,
+    "sort_radix_i32": 77777, "sort_bitonic_u32": 5000, "atomics": 100000, "matmul": 200, "nbody": 1000, "nbody_loop": 1000,
+    "host_loop": 333, "autograd_mlp": 48, "scatter_matmul": 40, "qr_inverse": 7, "pcgf_random": 10000,
+}
+
+
+@pytest.fixture(scope="module")
+def live_oracle(tmp_path_factory):
+    if not HAVE_ORACLE:
+        pytest.skip("oracle/_ref not present on this box")
+    out = tmp_path_factory.mktemp("oracle") / "live.npz"
+    specs = [f"{n}:{s}:7" for n, s in LIVE.items()]
+    r = subprocess.run([sys.executable, os.path.join(HERE, "run_case.py"), "cpu", str(out)] + specs, cwd=str(out.parent),
+                       capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    return np.load(out)
+
+
+@pytest.mark.parametrize("name", sorted(LIVE))
+def test_case_matches_live_oracle(tf_cuda, live_oracle, name):
+    spec = f"{name}:{LIVE[name]}:7"
+    want = []
+    while f"{spec}/{len(want)}" in live_oracle:
+        want.append(live_oracle[f"{spec}/{len(want)}"])
+    got = _run_cuda(tf_cuda, name, 7, LIVE[name])
+    cases.compare(cases.CASES[name], got, want)
