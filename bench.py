@@ -330,6 +330,7 @@ def main():
     ap.add_argument("--size", type=int, default=2048)
     ap.add_argument("--cpu-steps", type=int, default=40, help="steps of the CPU baseline sample (about 10-30 s of host work)")
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--quick", action="store_true", help="smaller extra workloads (development)")
     ap.add_argument("--workload", default="fluid", choices=["fluid", "nca"])
     args = ap.parse_args()
@@ -363,7 +364,7 @@ def main():
             "gpu_launches": int(res["launches"]), "clocks": res["clocks"], "roofline": res["roofline"], "e2e": res["e2e"],
             "top_kernels": res["records"],
         }
-        if world == 1:
+        if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args)
         if extra is not None:
             line["extra"] = extra
