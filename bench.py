@@ -333,6 +333,11 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--quick", action="store_true", help="smaller extra workloads (development)")
     ap.add_argument("--workload", default="fluid", choices=["fluid", "nca"])
+    ap.add_argument("--nca-batch", type=int, default=256, help="GLOBAL batch (split across ranks: strong scaling)")
+    ap.add_argument("--nca-grid", type=int, default=128)
+    ap.add_argument("--nca-pool", type=int, default=1024)
+    ap.add_argument("--nca-steps", type=int, default=25, help="CA steps per training iteration")
+    ap.add_argument("--nca-mono", action="store_true", help="run the reference's single program instead of the split step (1 GPU only)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

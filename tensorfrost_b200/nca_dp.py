@@ -1,0 +1,312 @@
+"""Data-parallel training of the reference's neural-cellular-automata example (BASELINE.json configs[4]) on 1/2/4/8 B200s.
+
+The reference trains NCA with ONE compiled program per iteration (examples/ML/NCA/nca.py:213-231 `optimization_step`): forward
+through `train_steps` CA steps, tf.grad, gradient-norm clipping and the Adam update all happen inside the traced program
+(nca.py:124-168, Python/TensorFrost/optimizers.py:104-147), and train.py:142-144 feeds the returned parameters back.  It has no
+distributed code.  Data parallelism needs the gradient exchange to sit BETWEEN tf.grad and the clip/Adam update, so the step is
+split into two programs traced from the reference's own code:
+
+  grad program    = CATrain.train_step with ModuleOptimizer._step replaced by "take tf.grad of every trainable parameter and
+                    pack [grads..., loss] into one flat fp32 tensor" (the pattern of the reference's tests/autograd_test.py:9-23)
+  exchange        = tf.cuda_allreduce(flat, 1/world): ncclAllReduce(sum) on the runtime stream + scale (libtfcuda comm.cu);
+                    7,820 gradient floats + 1 loss for CAModel = 31 KB -> one latency-bound collective, no bucketing
+  apply program   = ModuleOptimizer._step (unchanged reference code) with tf.grad replaced by "unpack from the flat tensor":
+                    clip by norm, Adam, parameter update; replicated and deterministic, so parameters stay bit-identical across
+                    ranks without any broadcast after step 0.
+
+Sharding: the batch dimension.  Global batch B -> B/world samples per rank; every rank owns a pool shard of
+POOL_SIZE/world states and draws its own batch ids; the model's RNG seed tensor is offset by rank so ranks do not draw the same
+noise.  The "restart the worst sample" rule (nca.py:143-149) is applied per rank.  One process per GPU (the backend is a
+process-global singleton), launched by torchrun; the NCCL id is broadcast through torch.distributed's store.
+
+With world == 1 the split step computes exactly what the reference's single program computes (tests/test_nca_gpu.py pins it
+against the oracle), and `mono=True` runs the reference's own unsplit program for comparison.
+"""
+import contextlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+from . import workloads
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# pure host-side helpers (covered by the CPU / gloo tests)
+# ----------------------------------------------------------------------------------------------------------------------
+def shard_sizes(global_batch, pool_size, world):
+    """Per-rank batch and pool shard.  Raises when the configuration does not divide (no silent truncation)."""
+    if global_batch % world or pool_size % world:
+        raise ValueError(f"global batch {global_batch} and pool {pool_size} must be divisible by world size {world}")
+    if global_batch // world > pool_size // world:
+        raise ValueError("per-rank batch exceeds the per-rank pool shard")
+    return global_batch // world, pool_size // world
+
+
+def draw_batch_ids(rng, pool_shard, batch):
+    """train.py:141: np.random.choice(POOL_SIZE, BATCH_SIZE, replace=False), per rank on its own shard."""
+    return rng.choice(pool_shard, batch, replace=False).astype(np.int32)
+
+
+def flat_layout(shapes):
+    """Offsets of each gradient inside the flat exchange buffer; the last slot is the loss."""
+    offsets, total = [], 0
+    for s in shapes:
+        offsets.append(total)
+        total += int(np.prod(s))
+    return offsets, total + 1
+
+
+def pack_flat(arrays, loss):
+    """numpy restatement of the in-program packing (tests compare the two)."""
+    return np.concatenate([np.asarray(a, np.float32).reshape(-1) for a in arrays] + [np.asarray([loss], np.float32)])
+
+
+def unpack_flat(flat, shapes):
+    offsets, total = flat_layout(shapes)
+    assert flat.size == total
+    return [flat[o:o + int(np.prod(s))].reshape(s) for o, s in zip(offsets, shapes)], float(flat[-1])
+
+
+def lr_schedule(iteration, lrs=(0.05, 0.02, 0.01, 0.002), steps=(0, 1000, 2000, 3000)):
+    """train.py:96-105 piecewise-linear schedule (train.py:142 multiplies it by 0.1)."""
+    for i in range(len(steps) - 1):
+        if steps[i] <= iteration < steps[i + 1]:
+            t = (iteration - steps[i]) / (steps[i + 1] - steps[i])
+            return lrs[i] * (1.0 - t) + lrs[i + 1] * t
+    return lrs[-1]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# tracing the two programs from the reference's code
+# ----------------------------------------------------------------------------------------------------------------------
+@contextlib.contextmanager
+def _patched(obj, name, value):
+    old = getattr(obj, name)
+    setattr(obj, name, value)
+    try:
+        yield
+    finally:
+        setattr(obj, name, old)
+
+
+def trainable(tf_module):
+    ps, req = tf_module.parameters(), tf_module.requires_grads_list()
+    return [p for p, r in zip(ps, req) if r]
+
+
+def build_programs(tf, nca, train_steps):
+    """Returns (grad_program, apply_program, mono_program_factory, grad_shapes)."""
+    grad_shapes = []
+
+    def make_train():
+        return nca.CATrain(train_steps=train_steps)
+
+    probe = make_train().opt.net
+    for p in trainable(probe):
+        grad_shapes.append(tuple(int(s) for s in p.shape))
+    offsets, flat_size = flat_layout(grad_shapes)
+
+    def grad_step():
+        train = make_train()
+        train.initialize_input()
+        batch_ids = tf.input([nca.BATCH_SIZE], tf.int32)
+        params = tf.input([-1], tf.float32)
+        train.opt.net.fire_rate = params[0]
+        flat = tf.buffer([flat_size], tf.float32)
+
+        def take_gradients(opt, loss):
+            for off, shape, p in zip(offsets, grad_shapes, trainable(opt.net)):
+                g = tf.grad(loss, p)
+                n = int(np.prod(shape))
+                g = tf.reshape(g, [n])
+                i, = g.indices
+                flat[i + off] = g
+            flat[flat_size - 1] = loss
+
+        with _patched(tf.optimizers.ModuleOptimizer, "_step", take_gradients):
+            loss, state = train.train_step(batch_ids)
+        return [train.pool, train.opt.net.seed, flat, state]
+
+    def apply_step():
+        opt = make_train().opt
+        opt.initialize_input()
+        flat = tf.input([flat_size], tf.float32)
+        params = tf.input([-1], tf.float32)
+        opt.learning_rate = params[0]
+        queue = []
+        for off, shape in zip(offsets, grad_shapes):
+            idx = tf.indices(list(shape))
+            lin = idx[0]
+            for d in range(1, len(shape)):
+                lin = lin * shape[d] + idx[d]
+            queue.append(flat[lin + off])
+
+        def exchanged_gradient(loss, param):
+            return queue.pop(0)
+
+        # optimizers.py binds `tf` to the extension module: patch tf.grad there only, and only while tracing
+        with _patched(tf.optimizers.tf, "grad", exchanged_gradient):
+            opt._step(None)
+        assert not queue, "the optimizer asked for fewer gradients than were exchanged"
+        return opt.parameters()
+
+    def mono_step():
+        return nca.optimization_step()
+
+    return grad_step, apply_step, mono_step, grad_shapes
+
+
+class NcaTrainer:
+    """One rank of the data-parallel NCA trainer (world == 1: plain single-GPU training)."""
+
+    def __init__(self, tf, global_batch=256, grid=128, pool_size=1024, train_steps=25, rank=0, world=1, seed=0, mono=False,
+                 channel_n=12, exchange=None, rank_seed_offset=1000003):
+        """exchange(flat_tensor, world) -> flat_tensor: the gradient exchange; default = tf.cuda_allreduce (NCCL, in place).
+        Tests on the CPU oracle backend inject a gloo exchange."""
+        self.tf, self.rank, self.world, self.mono = tf, rank, world, mono
+        self.exchange = exchange
+        self.batch, self.pool_shard = shard_sizes(global_batch, pool_size, world)
+        self.grid, self.train_steps = grid, train_steps
+        nca = workloads.load_nca(tf, self.batch, grid, pool_size=self.pool_shard, train_steps=train_steps, channel_n=channel_n)
+        self.nca = nca
+        grad_step, apply_step, mono_step, self.grad_shapes = build_programs(tf, nca, train_steps)
+        if mono:
+            import functools
+            nca.CATrain = functools.partial(nca.CATrain, train_steps=train_steps)
+            self.mono_program = tf.compile(mono_step)
+        else:
+            self.grad_program = tf.compile(grad_step)
+            self.apply_program = tf.compile(apply_step)
+        self.trainer = nca.CATrain(train_steps=train_steps) if not mono else nca.CATrain()
+        self.trainer.initialize_parameters()
+        self.opt = self.trainer.opt
+        self.model = self.opt.net
+        # deterministic initial weights identical on every rank (tf.Parameter's own init is unseeded): train.py:60-80 otherwise
+        rng = np.random.default_rng(seed)
+        upload = getattr(tf, "cuda_tensor", tf.tensor)
+        self._upload = upload
+        hidden = int(self.model.fc1.shape[1])
+        self.model.fc1 = upload((rng.standard_normal((channel_n * 4, hidden)) * np.sqrt(2.0 / (channel_n * 4))).astype(np.float32))
+        self.model.fc1_bias = upload(np.zeros(hidden, np.float32))
+        self.model.fc2 = upload(np.zeros((hidden, channel_n), np.float32))
+        self.model.fc2_bias = upload(np.zeros(channel_n, np.float32))
+        self.model.filters = upload(workloads.nca_filters())
+        self.model.seed = upload(np.array([rank_seed_offset * rank], np.uint32))  # per-rank RNG stream
+        self.trainer.image = upload(workloads.nca_target(grid, seed))
+        self.trainer.pool = upload(workloads.nca_pool(self.pool_shard, grid, channel_n))
+        self.ids_rng = np.random.default_rng(seed * 7919 + rank)
+        self.iteration = 0
+        self.fire_rate = float(nca.CELL_FIRE_RATE)
+
+    # -- one training iteration -----------------------------------------------------------------------------------
+    def step(self, batch_ids=None, lr=None, read_loss=False):
+        tf = self.tf
+        if batch_ids is None:
+            batch_ids = draw_batch_ids(self.ids_rng, self.pool_shard, self.batch)
+        if lr is None:
+            lr = 0.1 * lr_schedule(self.iteration)
+        self.iteration += 1
+        if self.mono:
+            outs = self.mono_program(self.trainer, batch_ids, np.array([lr, 0.0, self.fire_rate, 1.0], np.float32))
+            self.trainer.update_parameters(outs[:-2])
+            self.last_flat = None
+            return float(outs[-2].numpy[0]) if read_loss else None
+        pool, seed, flat, state = self.grad_program(self.trainer, batch_ids, np.array([self.fire_rate], np.float32))
+        self.trainer.pool = pool
+        self.model.seed = seed
+        if self.world > 1:
+            if self.exchange is not None:
+                flat = self.exchange(flat, self.world)
+            else:
+                tf.cuda_allreduce(flat, 1.0 / self.world)
+        new_params = self.apply_program(self.opt, flat, np.array([lr], np.float32))
+        self.opt.update_parameters(new_params)
+        self.last_flat, self.last_state = flat, state
+        if read_loss:
+            return float(np.array(flat.numpy)[-1])
+        return None
+
+    def parameters_numpy(self):
+        return [np.array(p.numpy) for p in self.opt.parameters()]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# communicator bootstrap: the NCCL unique id travels through torch.distributed's rendezvous store
+# ----------------------------------------------------------------------------------------------------------------------
+def init_comm(tf, rank, world):
+    if world == 1:
+        return None
+    import torch.distributed as dist
+    if rank == 0:
+        uid = tf.cuda_comm_unique_id()
+        box = [uid]
+    else:
+        box = [None]
+    dist.broadcast_object_list(box, src=0)
+    tf.cuda_comm_init(box[0], rank, world)
+    return box[0]
+
+
+def bench_main(args):
+    """bench.py --workload nca: K training iterations, strong scaling (global batch fixed, split across ranks).
+    value = samples/s over all ranks."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch  # before TensorFrost
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("gloo")  # control plane only: barrier, id broadcast, max-over-ranks
+    import tensorfrost_b200
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(1)
+    os.dup2(devnull, 1)
+    try:
+        tf = tensorfrost_b200.load()
+        init_comm(tf, rank, world)
+        t0 = time.perf_counter()
+        tr = NcaTrainer(tf, global_batch=args.nca_batch, grid=args.nca_grid, pool_size=args.nca_pool, train_steps=args.nca_steps,
+                        rank=rank, world=world, mono=args.nca_mono)
+        build_s = time.perf_counter() - t0
+        for _ in range(max(args.warmup, 3)):
+            tr.step()
+        tf.cuda_synchronize()
+        if dist is not None:
+            dist.barrier()
+        launches0 = tf.cuda_launch_count()
+        tf.cuda_timer_begin()
+        for _ in range(args.steps):
+            tr.step()
+        ms = tf.cuda_timer_end()
+        tf.cuda_synchronize()
+        launches = tf.cuda_launch_count() - launches0
+        loss = tr.step(read_loss=True)
+        if dist is not None:
+            import torch
+            t = torch.tensor([ms], dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            dist.barrier()
+    finally:
+        os.dup2(saved, 1)
+    if rank == 0:
+        samples = args.nca_batch * args.steps
+        line = {
+            "metric": "NCA training samples/s", "value": samples / (ms / 1e3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"NCA training (examples/ML/NCA), global batch {args.nca_batch} of {args.nca_grid}x{args.nca_grid}x12, "
+                                   f"{args.nca_steps} CA steps, pool {args.nca_pool}", "parallelism": f"dp{world}",
+                       "per_rank_batch": args.nca_batch // world, "exchange": "ncclAllReduce(sum) of 7821 fp32 + scale, once per step",
+                       "program": "reference single program" if args.nca_mono else "grad program -> allreduce -> apply program"},
+            "gpu_launches": int(launches), "loss_after": loss, "build_seconds": build_s,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
