@@ -9,6 +9,7 @@
 #include "tfcuda_internal.h"
 
 int tfcuda_matmul_tcgen05(const float* a, const float* b, float* c, size_t batch, size_t m, size_t n, size_t k, int mode);
+bool tfcuda_matmul_tcgen05_supported(const float* a, const float* b, const float* c, size_t m, size_t n, size_t k);
 
 namespace {
 
@@ -93,8 +94,10 @@ extern "C" int tfcuda_matmul(uint64_t a, uint64_t b, uint64_t c, size_t batch, s
 	const float* pa = reinterpret_cast<const float*>(a);
 	const float* pb = reinterpret_cast<const float*>(b);
 	float* pc = reinterpret_cast<float*>(c);
-	if (mode == 0 || mode == 1) return tfcuda_matmul_tcgen05(pa, pb, pc, batch, m, n, k, mode);
-	if (mode != 2) { tfcuda::set_error("tfcuda_matmul: unknown mode"); return 1; }
+	if (mode < 0 || mode > 2) { tfcuda::set_error("tfcuda_matmul: unknown mode"); return 1; }
+	// modes 0/1 need TMA-describable operands (16-byte aligned bases and row pitches, every batch slice); other shapes take the FFMA kernel
+	if (mode != 2 && tfcuda_matmul_tcgen05_supported(pa, pb, pc, m, n, k) && (batch == 1 || ((m * k) % 4 == 0 && (k * n) % 4 == 0 && (m * n) % 4 == 0)))
+		return tfcuda_matmul_tcgen05(pa, pb, pc, batch, m, n, k, mode);
 	tfcuda::ProfileScope prof("lib/matmul_ffma");
 	dim3 grid((unsigned)((n + BN - 1) / BN), (unsigned)((m + BM - 1) / BM), (unsigned)batch);
 	matmul_ffma_kernel<<<grid, MM_THREADS, 0, s.stream>>>(pa, pb, pc, (int)m, (int)n, (int)k);
