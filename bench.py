@@ -266,6 +266,9 @@ def bench_extra(tf, peaks, quick):
     ms = time_call(tf, lambda: tf.cuda_radix_sort(keys, vals), 5)
     out["radix_sort_pairs"] = {"n": n, "ms": ms, "gkeys_per_s": n / ms / 1e6, "roofline": {"bound": "hbm", "achieved": 68.0 * n / ms / 1e6, "peak": hbm,
                                "unit": "GB/s", "frac": 68.0 * n / ms / 1e6 / hbm}}
+    sort_prog = workloads.compile_sort(tf, with_values=True)  # tf.sort.radix inside a compiled program
+    ms = time_call(tf, lambda: sort_prog(keys, vals), 5)
+    out["radix_sort_pairs_program"] = {"n": n, "ms": ms, "gkeys_per_s": n / ms / 1e6, "note": "tf.sort.radix(keys, values) traced by tf.compile: one library call + output copies"}
     del keys, vals
     # ---- n-body, 262144 bodies: library kernel and the generic emitter on the reference program ----
     nb = 32768 if quick else 262144
@@ -286,11 +289,20 @@ def bench_extra(tf, peaks, quick):
         ms = time_call(tf, lambda: tf.cuda_reduce(a, -1, op), 20)
         out[f"reduce_{op}"] = {"shape": [m, m], "ms": ms, "roofline": {"bound": "hbm", "achieved": m * m * 4 / ms / 1e6, "peak": hbm, "unit": "GB/s",
                                "frac": m * m * 4 / ms / 1e6 / hbm}}
-    red = workloads.compile_row_reductions(tf, m)
-    ms = time_call(tf, lambda: red(a), 5)
-    out["reduce_emitted_4ops"] = {"shape": [m, m], "ms": ms, "gbs_one_read": m * m * 4 / ms / 1e6}
+    red = workloads.compile_row_reductions(tf, m)  # the compiled program: 4 library reductions -> 4 reads of A
+    ms = time_call(tf, lambda: red(a), 10)
+    out["reduce_program_4ops"] = {"shape": [m, m], "ms": ms, "roofline": {"bound": "hbm", "achieved": 4 * m * m * 4 / ms / 1e6, "peak": hbm, "unit": "GB/s",
+                                  "frac": 4 * m * m * 4 / ms / 1e6 / hbm, "note": "tf.sum/max/mean/norm in one compiled program, each a library call reading A once"}}
+    os.environ["TFCUDA_LIBRARY"] = "0"
+    red_generic = workloads.compile_row_reductions(tf, m)
+    os.environ.pop("TFCUDA_LIBRARY")
+    ms = time_call(tf, lambda: red_generic(a), 5)
+    out["reduce_program_4ops_generic_lowering"] = {"shape": [m, m], "ms": ms, "gbs_one_read": m * m * 4 / ms / 1e6}
     # ---- matmul 8192^2 ----
     b = tf.cuda_tensor(rng.random((m, m), dtype=np.float32))
+    mm_prog = workloads.compile_matmul(tf)
+    ms = time_call(tf, lambda: mm_prog(a, b), 10, warm=3)
+    out["matmul_program"] = {"shape": [m, m, m], "ms": ms, "tflops": 2.0 * m ** 3 / ms / 1e9, "note": "`a @ b` in a compiled program (library call, 3xTF32 mode by default)"}
     ms = time_call(tf, lambda: tf.cuda_matmul(a, b, 2), 3, warm=1)
     tf32_peak = peaks["bf16_tflops"] / 2
     out["matmul_ffma"] = {"shape": [m, m, m], "ms": ms, "tflops": 2.0 * m ** 3 / ms / 1e9,

@@ -29,7 +29,7 @@ if [ ! -f "$SCRATCH/.refhash" ] || [ "$(cat "$SCRATCH/.refhash")" != "$REFHASH" 
   echo "$REFHASH" > "$SCRATCH/.refhash"
 else
   # incremental: refresh only our own sources
-  for rel in Backend/Backends/CUDA/CUDA.h Backend/Backends/CUDA/CudaBackend.cpp Backend/Backends/CUDA/CudaPython.cpp Backend/CodeGen/Langs/CUDA.cpp; do
+  for rel in Backend/Backends/CUDA/CUDA.h Backend/Backends/CUDA/CudaBackend.cpp Backend/Backends/CUDA/CudaLibrary.cpp Backend/Backends/CUDA/CudaPython.cpp Backend/CodeGen/Langs/CUDA.cpp; do
     cmp -s "$HERE/overlay/$rel" "$S/TensorFrost/$rel" || cp "$HERE/overlay/$rel" "$S/TensorFrost/$rel"
   done
 fi

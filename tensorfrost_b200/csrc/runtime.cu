@@ -641,6 +641,10 @@ int tfcuda_launch(size_t kernel_id, const uint64_t* mem, size_t n_mem, const uin
 		return 1;
 	}
 	KernelEntry& e = g_kernels[kernel_id];
+	if (e.library_op) {
+		set_error("tfcuda_launch: kernel " + std::to_string(kernel_id) + " is a library call; it is dispatched by the backend glue (tfcuda_matmul / tfcuda_reduce / ...), not launched");
+		return 1;
+	}
 	if (n_mem != e.n_mem || n_var != e.n_var) {
 		set_error("tfcuda_launch: kernel " + std::to_string(kernel_id) + " expects " + std::to_string(e.n_mem) + " buffers / " + std::to_string(e.n_var) +
 		          " variables, got " + std::to_string(n_mem) + " / " + std::to_string(n_var));

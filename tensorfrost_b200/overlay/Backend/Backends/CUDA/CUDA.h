@@ -14,6 +14,7 @@
 
 #include "../../KernelManager.h"
 #include "../../TensorMemory.h"
+#include "Tensor/Tensor.h"
 
 namespace TensorFrost {
 
@@ -26,6 +27,23 @@ void StartCUDA();
 void StopCUDA();
 void CudaFinish();
 void CudaRegion(const char* name, bool begin);
+
+// ---- library calls inside compiled programs (CudaLibrary.cpp) ---------------------------------------------------------
+// One hand-written libtfcuda kernel standing in for a lowered algorithmic op; `inputs` / `outputs` are binding indices into
+// the dispatch's tensor list (rw bindings first, then ro: Compiler/KernelGen.h:36-45).
+struct CudaLibraryCall {
+	std::string op;            // "reduce" | "scan" | "matmul" | "sort"
+	std::vector<int> params;   // reduce: {TFCUDA_RED_*, internal axis}; scan: {internal axis}; matmul: {mode}; sort: {has_values, max_bits}
+	std::vector<int> inputs;
+	std::vector<int> outputs;
+};
+void InstallCudaLibraryLowerings();                     // replaces entries of implementation_functions (Compiler/Implementations.cpp:648)
+bool CudaLibraryWantsReduction(Node* node);             // consulted by IR::OptimizeReductions (Steps/Optimization.cpp:471) before it stages a reduction
+std::vector<Tensor*> CudaLibrarySort(const Tensor* keys, const Tensor* values, int max_bits);
+bool IsCudaLibraryKernel(Kernel* kernel);
+void RegisterCudaLibraryKernel(Kernel* kernel);
+const CudaLibraryCall* FindCudaLibraryCall(size_t kernel_id);
+void DispatchCudaLibraryCall(const CudaLibraryCall& call, const TFDispatchInfo& info);
 
 class TFCudaBuffer : public TFBufferTemplate {
  public:

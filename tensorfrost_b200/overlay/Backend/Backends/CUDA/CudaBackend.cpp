@@ -68,7 +68,7 @@ void CudaKernelManager::CompileProgram(Program* program) {
 		for (int d = 0; d < 3; d++) s.group[d] = (unsigned)group[d];
 		s.n_mem = (unsigned)kernel.GetMemoryBindings().size();
 		s.n_var = (unsigned)kernel.var_names.size();
-		s.library_op = 0;
+		s.library_op = FindCudaLibraryCall(kernel.kernel_id_) != nullptr ? 1 : 0;  // no source: dispatched by DispatchCudaLibraryCall
 		sources.push_back(s);
 	}
 	if (tfcuda_compile_kernels(sources.data(), sources.size(), cudaKernelCompileOptions.c_str()) != 0) {
@@ -77,6 +77,10 @@ void CudaKernelManager::CompileProgram(Program* program) {
 }
 
 void CudaKernelManager::DispatchKernel(TFDispatchInfo info) {
+	if (const CudaLibraryCall* call = FindCudaLibraryCall(info.kernel_id)) {
+		DispatchCudaLibraryCall(*call, info);
+		return;
+	}
 	uint64_t ptrs[256];
 	if (info.read_write_count > 256) throw std::runtime_error("CUDA backend: too many buffers in dispatch");
 	for (size_t i = 0; i < info.read_write_count; i++) {

@@ -151,6 +151,19 @@ void CudaDefinitions(py::module& m) {
 	}, py::arg("tensor"), py::arg("scale") = 1.0f, "In-place sum-allreduce over the NCCL communicator, then multiply by scale");
 	m.def("cuda_comm_destroy", []() { tfcuda_comm_destroy(); });
 
+	// ---- library call inside a traced program: tf.sort.radix on this backend (see overlay/python/install.py) ----------
+	m.def("cuda_library_active", []() {
+		const char* v = getenv("TFCUDA_LIBRARY");
+		return current_kernel_lang == CodeGenLang::CUDA && !(v && atoi(v) == 0);
+	}, "True when algorithmic ops of traced programs are lowered to libtfcuda library calls (kernel language is CUDA)");
+	m.def("cuda_library_sort", [](const PyTensor& keys, py::object values, int max_bits) -> py::object {
+		const Tensor* v = values.is_none() ? nullptr : &values.cast<const PyTensor&>().Get();
+		std::vector<Tensor*> out = CudaLibrarySort(&keys.Get(), v, max_bits);
+		if (out.size() == 1) return py::cast(PT(*out[0]));
+		return py::make_tuple(PT(*out[0]), PT(*out[1]));
+	}, py::arg("keys"), py::arg("values") = py::none(), py::arg("max_bits") = 32,
+	   "Traced stable LSD radix sort of a 1-D tensor (one libtfcuda library call in the compiled program)");
+
 	// ---- library kernels on TensorMemory ------------------------------------------------------------
 	m.def("cuda_radix_sort", [](const PyTensorMemory& keys, py::object values, int max_bits) -> py::object {
 		RequireCuda("cuda_radix_sort");

@@ -23,6 +23,7 @@
 // The whole argument block travels in constant param space (one cuLaunchKernel parameter), so a
 // dispatch needs no device-side pointer table and no UBO upload (cf. OpenGL/KernelManager.h:127-141).
 #include "Backend/CodeGen/Generators.h"
+#include "Backend/Backends/CUDA/CUDA.h"
 
 namespace TensorFrost {
 using namespace std;
@@ -92,6 +93,16 @@ void GenerateCUDAKernel(Program* program, Kernel* kernel) {
 	vector<int> group = kernel->root->group_size;
 	while (group.size() < 3) group.push_back(1);
 	const int threads = group[0] * group[1] * group[2];
+
+	if (IsCudaLibraryKernel(kernel)) {
+		// a library call (CudaLibrary.cpp): record which binding plays which role; there is no source to emit
+		RegisterCudaLibraryKernel(kernel);
+		kernel->generated_header_ = "";
+		kernel->generated_bindings_ = "";
+		kernel->generated_main_ = "// " + kname + ": " + kernel->root->debug_name + " -> hand-written kernel in libtfcuda.so\n";
+		kernel->full_generated_code_ = kernel->generated_main_;
+		return;
+	}
 
 	// the body first: generating it may rename nodes (RegenerateNodeName), and binding names below must
 	// be read after that

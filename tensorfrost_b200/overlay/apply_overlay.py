@@ -53,7 +53,7 @@ def main():
     overlay = repo / "tensorfrost_b200" / "overlay"
 
     # 1. our sources: backend glue + emitter (TensorFrost/CMakeLists.txt globs *.cpp recursively)
-    for rel in ["Backend/Backends/CUDA/CUDA.h", "Backend/Backends/CUDA/CudaBackend.cpp",
+    for rel in ["Backend/Backends/CUDA/CUDA.h", "Backend/Backends/CUDA/CudaBackend.cpp", "Backend/Backends/CUDA/CudaLibrary.cpp",
                 "Backend/Backends/CUDA/CudaPython.cpp", "Backend/CodeGen/Langs/CUDA.cpp"]:
         dst = tf / rel
         dst.parent.mkdir(parents=True, exist_ok=True)
@@ -79,6 +79,9 @@ def main():
                     "\t\t\tglobal_memory_manager = new CudaMemoryManager();\n"
                     "\t\t\tglobal_kernel_manager = new CudaKernelManager();\n"
                     "\t\t\tbreak;\n")
+    # library lowerings follow the kernel LANGUAGE, so codegen mode with kernel_lang=tf.cuda_lang shows the same host program
+    p.insert_after("\tif (kernelType != CodeGenLang::None) {\n\t\tcurrent_kernel_lang = kernelType;\n\t}\n",
+                   "\tif (current_kernel_lang == CodeGenLang::CUDA) InstallCudaLibraryLowerings();\n")
     p.insert_after("auto start_time = chrono::high_resolution_clock::now();\n",
                    "\tif (current_backend == BackendType::CUDA) {\n"
                    "\t\t((CudaKernelManager*)global_kernel_manager)->CompileProgram(program);\n"
@@ -97,6 +100,12 @@ def main():
     p = Patch(tf / "Backend" / "CodeGen" / "Generators.h")
     p.insert_after("void GenerateGLSLKernel(Program* program, Kernel* kernel);\n",
                    "void GenerateCUDAKernel(Program* program, Kernel* kernel);\n")
+    p.save()
+
+    # 4b. reductions the CUDA library takes whole are not split into the staged two-pass form (Steps/Optimization.cpp:471-510)
+    p = Patch(tf / "Compiler" / "Steps" / "Optimization.cpp")
+    p.insert_before("void IR::OptimizeReductions() {", "bool CudaLibraryWantsReduction(Node* node);  // Backend/Backends/CUDA/CudaLibrary.cpp\n\n")
+    p.insert_after("\t\tint axis = (int)node->data[0];\n", "\t\tif (CudaLibraryWantsReduction(node)) continue;\n")
     p.save()
 
     # 5. python bindings (Frontend/Python/PybindModule.cpp)

@@ -24,23 +24,50 @@ pytestmark = pytest.mark.gpu
 
 _programs = {}
 
+# Both lowerings of the algorithmic ops are covered: "library" = matmul / long reductions / scans / tf.sort.radix become
+# libtfcuda library calls inside the compiled program (overlay CudaLibrary.cpp); "generic" = the reference's own fused serial
+# loops run through the CUDA emitter (TFCUDA_LIBRARY=0, read at trace time).
+LOWERINGS = ["library", "generic"]
+USES_LIBRARY = {"row_reductions", "int_reductions", "prefix_sum", "sort_radix_u32", "sort_radix_f32", "sort_radix_i32", "matmul", "qr_inverse",
+                "autograd_mlp"}
 
-def _run_cuda(tf, name, seed, size):
-    outs, prog = cases.run_case(tf, name, seed=seed, size=size, program=_programs.get(name))
-    _programs[name] = prog
+
+def _run_cuda(tf, name, seed, size, lowering="library"):
+    os.environ["TFCUDA_LIBRARY"] = "1" if lowering == "library" else "0"
+    try:
+        outs, prog = cases.run_case(tf, name, seed=seed, size=size, program=_programs.get((name, lowering)))
+    finally:
+        os.environ.pop("TFCUDA_LIBRARY", None)
+    _programs[(name, lowering)] = prog
     return outs
 
 
-@pytest.mark.parametrize("name", sorted(cases.CASES))
-def test_case_matches_golden(tf_cuda, name):
+def _lowerings(name):
+    return LOWERINGS if name in USES_LIBRARY else ["generic"]
+
+
+@pytest.mark.parametrize("name,lowering", [(n, l) for n in sorted(cases.CASES) for l in _lowerings(n)])
+def test_case_matches_golden(tf_cuda, name, lowering):
     path = os.path.join(GOLDEN, f"{name}.npz")
     assert os.path.exists(path), f"no golden fixture for {name}; run tests/golden/make_golden.py"
     g = np.load(path)
     want = []
     while f"out{len(want)}" in g:
         want.append(g[f"out{len(want)}"])
-    got = _run_cuda(tf_cuda, name, int(g["seed"]), int(g["size"]))
+    got = _run_cuda(tf_cuda, name, int(g["seed"]), int(g["size"]), lowering)
     cases.compare(cases.CASES[name], got, want)
+
+
+def test_library_lowering_is_really_used(tf_cuda):
+    """The library cases must contain library-call kernels (no silent generic path), and TFCUDA_LIBRARY=0 must remove them."""
+    for name in sorted(USES_LIBRARY):
+        _run_cuda(tf_cuda, name, 0, None, "library")
+        prog = _programs[(name, "library")]
+        kernels = prog.get_kernels() if hasattr(prog, "get_kernels") else None
+        if kernels is not None:
+            assert any("tfcuda_lib:" in k for k in kernels), f"{name}: no library call in the compiled program"
+    _run_cuda(tf_cuda, "matmul", 0, None, "generic")
+    assert not any("tfcuda_lib:" in k for k in _programs[("matmul", "generic")].get_kernels())
 
 
 # a second size/seed per case, checked against a live oracle process
@@ -64,11 +91,11 @@ def live_oracle(tmp_path_factory):
     return np.load(out)
 
 
-@pytest.mark.parametrize("name", sorted(LIVE))
-def test_case_matches_live_oracle(tf_cuda, live_oracle, name):
+@pytest.mark.parametrize("name,lowering", [(n, l) for n in sorted(LIVE) for l in _lowerings(n)])
+def test_case_matches_live_oracle(tf_cuda, live_oracle, name, lowering):
     spec = f"{name}:{LIVE[name]}:7"
     want = []
     while f"{spec}/{len(want)}" in live_oracle:
         want.append(live_oracle[f"{spec}/{len(want)}"])
-    got = _run_cuda(tf_cuda, name, 7, LIVE[name])
+    got = _run_cuda(tf_cuda, name, 7, LIVE[name], lowering)
     cases.compare(cases.CASES[name], got, want)
