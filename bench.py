@@ -349,6 +349,7 @@ def main():
     ap.add_argument("--nca-grid", type=int, default=128)
     ap.add_argument("--nca-pool", type=int, default=1024)
     ap.add_argument("--nca-steps", type=int, default=25, help="CA steps per training iteration")
+    ap.add_argument("--nca-profile", action="store_true", help="add a per-kernel profile of one iteration to the NCA line")
     ap.add_argument("--nca-mono", action="store_true", help="run the reference's single program instead of the split step (1 GPU only)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -18,6 +18,13 @@ typedef unsigned int uint;
 
 #define TF_DEV static __device__ __forceinline__
 
+// read-only buffer bindings; build kernels with -DTF_NO_RESTRICT when a program binds one buffer both read-only and writable
+#ifdef TF_NO_RESTRICT
+#define TF_RO const uint*
+#else
+#define TF_RO const uint* __restrict__
+#endif
+
 // ---- bit casts (CPP.cpp:53-96) ------------------------------------------------------------
 TF_DEV float asfloat(uint x) { return __uint_as_float(x); }
 TF_DEV float asfloat(int x) { return __int_as_float(x); }

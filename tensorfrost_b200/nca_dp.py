@@ -286,6 +286,17 @@ def bench_main(args):
         tf.cuda_synchronize()
         launches = tf.cuda_launch_count() - launches0
         loss = tr.step(read_loss=True)
+        top = None
+        if getattr(args, "nca_profile", False) and rank == 0:
+            tf.cuda_profile_reset()
+            tf.cuda_profile_enable(True)
+            tr.step()
+            tf.cuda_profile_enable(False)
+            recs = sorted(tf.cuda_profile_records(), key=lambda r: -r["total_ms"])
+            total = sum(r["total_ms"] for r in recs)
+            top = [{"name": r["name"], "launches": r["launches"], "ms": round(r["total_ms"], 3), "share": round(r["total_ms"] / total, 4),
+                    "gbs": round(r["bytes"] / max(r["total_ms"], 1e-9) / 1e6, 1)} for r in recs[:24]]
+            top.append({"name": "TOTAL", "launches": sum(r["launches"] for r in recs), "ms": round(total, 3), "gb": round(sum(r["bytes"] for r in recs) / 1e9, 2)})
         if dist is not None:
             import torch
             t = torch.tensor([ms], dtype=torch.float64)
@@ -306,6 +317,8 @@ def bench_main(args):
                        "program": "reference single program" if args.nca_mono else "grad program -> allreduce -> apply program"},
             "gpu_launches": int(launches), "loss_after": loss, "build_seconds": build_s,
         }
+        if top is not None:
+            line["top_kernels"] = top
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -159,7 +159,9 @@ void LowerMatmul(Tensors& outputs, map<int, const Tensor*> inputs, const Tensor*
 	const Tensor* a = inputs[0];
 	const Tensor* b = inputs[1];
 	int da = a->GetDimension(), db = b->GetDimension();
-	bool shapes_ok = da >= 2 && db >= 2 && (db == 2 || db == da);
+	// batched operands (B with batch dims, e.g. the per-sample products of matmul's own VJP) stay on the generic lowering: one library
+	// launch per batch slice would be launch-bound for the many-small-slices shapes autodiff produces
+	bool shapes_ok = da >= 2 && db == 2;
 	bool types_ok = a->node_->format.type == TFType::Float && b->node_->format.type == TFType::Float;
 	if (!LibraryEnabled() || !shapes_ok || !types_ok || EnvInt("TFCUDA_LIBRARY_MATMUL", 1) == 0) {
 		g_generic["matmul"](outputs, inputs, tensor, axes);

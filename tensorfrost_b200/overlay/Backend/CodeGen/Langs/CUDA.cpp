@@ -24,6 +24,7 @@
 // dispatch needs no device-side pointer table and no UBO upload (cf. OpenGL/KernelManager.h:127-141).
 #include "Backend/CodeGen/Generators.h"
 #include "Backend/Backends/CUDA/CUDA.h"
+#include "Backend/Backend.h"
 
 namespace TensorFrost {
 using namespace std;
@@ -65,6 +66,36 @@ class CUDAGenerator : public CodeGenerator {
 		return it->second + "((uint*)" + memory_name + ", " + address + ", (" + input_type_name + ")(" + input + "))";
 	}
 };
+
+}  // namespace
+
+// Default thread-block shape for kernels the user did not size (consulted by IR::LinearBlockModeIndices, Steps/GraphOps.cpp:1143-1166,
+// which otherwise picks 256 / 16x16 / 8x8x8).  On a GPU the innermost kernel dimension is the contiguous one in memory, so a warp
+// should span 32 consecutive innermost indices (one 128-byte line per row) instead of 16 or 8; the remaining threads go to the
+// outer dimensions.  const_shape[i] > 0 where the extent is a compile-time constant (blocks never exceed it).  Returns {} for
+// other kernel languages.
+vector<int> CudaDefaultGroupSize(int dims, const vector<int>& const_shape) {
+	if (current_kernel_lang != CodeGenLang::CUDA) return {};
+	auto pow2_floor = [](int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; };
+	auto extent = [&](int i) { return (i < (int)const_shape.size() && const_shape[i] > 0) ? const_shape[i] : (1 << 30); };
+	const int target = 256;
+	vector<int> group;
+	int g0 = min(extent(0), dims == 1 ? target : 32);
+	group.push_back(g0);
+	if (dims == 1) return group;
+	int remaining = max(1, target / g0);
+	if (dims == 2) {
+		group.push_back(min(extent(1), pow2_floor(remaining)));
+		return group;
+	}
+	int g1 = min(extent(1), max(1, pow2_floor(remaining) / 2));
+	group.push_back(g1);
+	remaining = max(1, target / (g0 * g1));
+	group.push_back(min(min(extent(2), pow2_floor(remaining)), 64));
+	return group;
+}
+
+namespace {
 
 string CudaSharedDeclaration(const string& name, const string& type_name, int size) {
 	return "  __shared__ " + type_name + " " + name + "[" + to_string(size) + "];\n";
@@ -117,8 +148,12 @@ void GenerateCUDAKernel(Program* program, Kernel* kernel) {
 	string main_code = "extern \"C\" __global__ void __launch_bounds__(" + to_string(threads) + ") " + kname +
 	                   "(const __grid_constant__ " + args_t + " tf_a)\n{\n";
 	main_code += GetGroupBufferDeclarations(kernel, CudaSharedDeclaration);
-	main_code += GetBufferDeclarations(kernel, [](const string& name, const string& type_name, size_t binding) {
-		return "  uint* " + name + "_mem = tf_a.mem[" + to_string(binding) + "];\n";
+	// read-only bindings (Kernel::read_only_memory come after the rw ones, KernelGen.h:36-45) are declared through TF_RO
+	// (= const uint* __restrict__, prelude.cuh): loads take the non-coherent path and may be hoisted / batched by the compiler
+	const size_t n_rw = kernel->read_write_memory.size();
+	main_code += GetBufferDeclarations(kernel, [n_rw](const string& name, const string& type_name, size_t binding) {
+		const string type = binding >= n_rw ? "TF_RO " : "uint* ";
+		return "  " + type + name + "_mem = tf_a.mem[" + to_string(binding) + "];\n";
 	});
 	for (size_t i = 0; i < n_var; i++) {
 		main_code += "  " + kernel->var_types[i] + " var_" + kernel->var_names[i] + " = as" + kernel->var_types[i] +
