@@ -17,6 +17,7 @@
 #include <unistd.h>
 
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <sstream>
@@ -66,34 +67,56 @@ static Pool g_pool;
 
 static size_t round_words(size_t words) { return (words + 63) & ~size_t(63); }
 
+// Guard bands.  The reference compiler fuses a user load (Clamp mode) into the Unsafe load of its reduction lowering
+// (Compiler/Implementations.cpp:293) and the clamp is lost: e.g. NCA's max_neighbor_alpha (examples/ML/NCA/nca.py:45-48) reads one
+// image row before / after its tensor, on the reference's own C++ backend too.  What such a read returns is whatever lies next to
+// the tensor, so results would depend on the allocation history of the process.  Every tensor buffer therefore sits between two
+// zero-filled bands (zeroed once, when the buffer is created; emitted kernels never write out of range): reads that overshoot by
+// less than the band see zeros - the value a fresh heap gives the reference - independent of what ran before.
+static size_t guard_bytes() {
+	static const size_t g = [] {
+		const char* v = getenv("TFCUDA_GUARD_BYTES");
+		size_t b = v ? (size_t)strtoull(v, nullptr, 0) : (size_t)16384;
+		return (b + 255) & ~size_t(255);
+	}();
+	return g;
+}
+
 static Buffer* create_buffer(size_t words) {
 	require_init();
 	if (words == 0) throw std::invalid_argument("tfcuda: trying to allocate a buffer with size 0");
 	void* p = nullptr;
-	cudaError_t e = cudaMallocAsync(&p, words * sizeof(uint32_t), g_state.stream);
+	const size_t guard = guard_bytes();
+	const size_t payload = (words * sizeof(uint32_t) + 255) & ~size_t(255);
+	const size_t total = payload + 2 * guard;
+	cudaError_t e = cudaMallocAsync(&p, total, g_state.stream);
 	if (e != cudaSuccess) {
 		// the pool may be holding memory another size class could use: trim and retry once
 		cudaStreamSynchronize(g_state.stream);
 		cudaMemPool_t mp;
 		if (cudaDeviceGetDefaultMemPool(&mp, g_state.device) == cudaSuccess) cudaMemPoolTrimTo(mp, 0);
 		(void)cudaGetLastError();
-		e = cudaMallocAsync(&p, words * sizeof(uint32_t), g_state.stream);
+		e = cudaMallocAsync(&p, total, g_state.stream);
 	}
 	if (e != cudaSuccess) {
 		std::string m = "tfcuda: device allocation of " + std::to_string(words * 4) + " bytes failed: " + cuda_err(e);
 		set_error(m);
 		throw std::runtime_error(m);
 	}
+	if (guard) {
+		cudaMemsetAsync(p, 0, guard, g_state.stream);
+		cudaMemsetAsync(static_cast<char*>(p) + guard + words * sizeof(uint32_t), 0, total - guard - words * sizeof(uint32_t), g_state.stream);
+	}
 	Buffer* b = new Buffer();
 	b->base.size = words;
-	b->dptr = reinterpret_cast<uint64_t>(p);
+	b->dptr = reinterpret_cast<uint64_t>(p) + guard;
 	g_pool.allocated_words += words;
 	return b;
 }
 
 static void destroy_buffer(Buffer* b) {
 	if (!b) return;
-	if (b->dptr && g_state.initialized) cudaFreeAsync(reinterpret_cast<void*>(b->dptr), g_state.stream);
+	if (b->dptr && g_state.initialized) cudaFreeAsync(reinterpret_cast<void*>(b->dptr - guard_bytes()), g_state.stream);
 	g_pool.allocated_words -= b->base.size;
 	delete b;
 }

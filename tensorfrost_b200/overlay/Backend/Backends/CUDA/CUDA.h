@@ -53,9 +53,14 @@ class TFCudaBuffer : public TFBufferTemplate {
 	explicit TFCudaBuffer(size_t size);
 	~TFCudaBuffer();
 
+	// called by TensorMemoryManager::AllocateTensor for every (re)allocation (Backend/TensorMemory.cpp:43-56): also the hook of
+	// the TFCUDA_POISON debugging aid, which fills every newly handed-out buffer with a NaN pattern so that programs reading
+	// memory they never wrote fail deterministically instead of depending on what the pool recycled
 	void UpdateName(const char* new_name) override {
 		if (new_name != nullptr) name = new_name;
+		Poison();
 	}
+	void Poison();
 	void SetDataAtOffset(size_t offset, const vector<uint32_t>& data) override;
 	void GetDataAtOffset(size_t offset, size_t size, uint32_t* data) override;
 	uint64_t GetNative() const { return device_ptr; }

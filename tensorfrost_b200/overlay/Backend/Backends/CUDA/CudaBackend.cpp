@@ -1,5 +1,7 @@
 // Glue between the reference's backend interfaces and libtfcuda.so (see CUDA.h).
 // Errors are thrown as std::runtime_error, the reference's error contract (Backend/Backend.cpp:166-170).
+#include <cstdlib>
+
 #include "CUDA.h"
 
 #define TFCUDA_NO_ABI_STRUCTS  // TFBuffer/TFTensor/... come from Backend/TensorMemory.h here
@@ -41,6 +43,13 @@ TFCudaBuffer::TFCudaBuffer(size_t size) : TFBufferTemplate(size) {
 	if (dev == nullptr) Fail("cannot allocate " + std::to_string(size * 4) + " bytes");
 	handle = dev;
 	device_ptr = tfcuda_buffer_device_ptr(dev);
+}
+
+void TFCudaBuffer::Poison() {
+	// TFCUDA_POISON=1: quiet-NaN pattern; TFCUDA_POISON=0x<word>: that word (e.g. 0x3f800000 = 1.0f, which unlike NaN passes `>` tests)
+	static const char* env = getenv("TFCUDA_POISON");
+	static const unsigned long word = env ? strtoul(env, nullptr, 0) : 0;
+	if (word != 0 && tfcuda_memset32(device_ptr, word == 1 ? 0x7fc0dead : (uint32_t)word, size) != 0) Fail("poison fill failed");
 }
 
 TFCudaBuffer::~TFCudaBuffer() { tfcuda_buffer_destroy((TFBuffer*)handle); }

@@ -213,16 +213,14 @@ void InstallCudaLibraryLowerings() {
 vector<Tensor*> CudaLibrarySort(const Tensor* keys, const Tensor* values, int max_bits) {
 	if (keys->GetDimension() != 1) throw std::runtime_error("cuda radix sort: keys must be one-dimensional");
 	Tensors shape = keys->GetShape();
-	const Tensor& n = *shape[0];
-	// scratch words: tfcuda_radix_sort_temp_words(n) = 2n + 4*256 + 64 + 4*ceil(n/8192)*256 + 64
-	const Tensor& temp_words = n * Tensor::Constant(2) + ((n + Tensor::Constant(8191)) / Tensor::Constant(8192)) * Tensor::Constant(1024) + Tensor::Constant(1152);
+	// the sort's scratch is NOT a program buffer: the compiler prunes memory that is never loaded; DispatchCudaLibraryCall takes it
+	// from the runtime's stream-ordered pool for the duration of the call instead
 	vector<const Tensor*> inputs = {keys};
 	vector<OutputSpec> outputs = {{shape, keys->node_->format}};
 	if (values != nullptr) {
 		inputs.push_back(values);
 		outputs.push_back({shape, values->node_->format});
 	}
-	outputs.push_back({{&temp_words}, TFTypeUint32});
 	string marker = string(kMarker) + "sort:" + to_string(values != nullptr ? 1 : 0) + ":" + to_string(max_bits);
 	vector<Tensor*> bufs = EmitLibraryCall(marker, inputs, outputs);
 	vector<Tensor*> result;
@@ -301,14 +299,16 @@ void DispatchCudaLibraryCall(const CudaLibraryCall& call, const TFDispatchInfo& 
 		Check(tfcuda_matmul(Ptr(a), Ptr(b), Ptr(c), batch, m, n, k, call.params[0]), "matmul");
 	} else if (call.op == "sort") {
 		bool has_values = call.params.size() > 0 && call.params[0] != 0;
-		need(has_values ? 2 : 1, has_values ? 3 : 2, 2);
+		need(has_values ? 2 : 1, has_values ? 2 : 1, 2);
 		const TFTensor& keys = tensor(call.inputs[0]);
 		size_t n = Extent(keys, 0, keys.dim);
 		if (n == 0) return;
-		const TFTensor& temp = tensor(call.outputs[has_values ? 2 : 1]);
-		if (Extent(temp, 0, temp.dim) < tfcuda_radix_sort_temp_words(n)) throw std::runtime_error("CUDA backend: radix sort scratch too small");
-		Check(tfcuda_radix_sort(Ptr(keys), Ptr(tensor(call.outputs[0])), has_values ? Ptr(tensor(call.inputs[1])) : 0,
-		                        has_values ? Ptr(tensor(call.outputs[1])) : 0, n, (int)keys.format.type, call.params[1], Ptr(temp)), "radix_sort");
+		uint64_t temp = tfcuda_malloc(tfcuda_radix_sort_temp_words(n) * 4);  // cudaMallocAsync on the runtime stream: pool hit after warm-up
+		if (!temp) throw std::runtime_error(string("CUDA backend: radix sort scratch: ") + tfcuda_last_error());
+		int rc = tfcuda_radix_sort(Ptr(keys), Ptr(tensor(call.outputs[0])), has_values ? Ptr(tensor(call.inputs[1])) : 0,
+		                           has_values ? Ptr(tensor(call.outputs[1])) : 0, n, (int)keys.format.type, call.params[1], temp);
+		tfcuda_free(temp);  // stream-ordered: released after the sort's kernels
+		Check(rc, "radix_sort");
 	} else {
 		throw std::runtime_error("CUDA backend: unknown library call " + call.op);
 	}

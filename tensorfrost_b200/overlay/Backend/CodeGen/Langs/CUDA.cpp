@@ -22,6 +22,8 @@
 //
 // The whole argument block travels in constant param space (one cuLaunchKernel parameter), so a
 // dispatch needs no device-side pointer table and no UBO upload (cf. OpenGL/KernelManager.h:127-141).
+#include <cstdlib>
+
 #include "Backend/CodeGen/Generators.h"
 #include "Backend/Backends/CUDA/CUDA.h"
 #include "Backend/Backend.h"
@@ -76,6 +78,9 @@ class CUDAGenerator : public CodeGenerator {
 // other kernel languages.
 vector<int> CudaDefaultGroupSize(int dims, const vector<int>& const_shape) {
 	if (current_kernel_lang != CodeGenLang::CUDA) return {};
+	if (const char* v = getenv("TFCUDA_DEFAULT_GROUP")) {
+		if (atoi(v) == 0) return {};  // debugging aid: the reference's own 256 / 16x16 / 8x8x8 defaults
+	}
 	auto pow2_floor = [](int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; };
 	auto extent = [&](int i) { return (i < (int)const_shape.size() && const_shape[i] > 0) ? const_shape[i] : (1 << 30); };
 	const int target = 256;
@@ -150,7 +155,8 @@ void GenerateCUDAKernel(Program* program, Kernel* kernel) {
 	main_code += GetGroupBufferDeclarations(kernel, CudaSharedDeclaration);
 	// read-only bindings (Kernel::read_only_memory come after the rw ones, KernelGen.h:36-45) are declared through TF_RO
 	// (= const uint* __restrict__, prelude.cuh): loads take the non-coherent path and may be hoisted / batched by the compiler
-	const size_t n_rw = kernel->read_write_memory.size();
+	const char* ro_env = getenv("TFCUDA_RO");  // debugging aid: TFCUDA_RO=0 declares every binding as plain uint*
+	const size_t n_rw = (ro_env && atoi(ro_env) == 0) ? n_mem : kernel->read_write_memory.size();
 	main_code += GetBufferDeclarations(kernel, [n_rw](const string& name, const string& type_name, size_t binding) {
 		const string type = binding >= n_rw ? "TF_RO " : "uint* ";
 		return "  " + type + name + "_mem = tf_a.mem[" + to_string(binding) + "];\n";
