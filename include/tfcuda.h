@@ -233,6 +233,11 @@ int tfcuda_scatter_add(uint64_t dst, uint64_t index, uint64_t src, size_t n, siz
  * mode 0: tcgen05 kind::tf32 (1e-3 class); mode 1: 3xTF32 split (fp32-accurate); mode 2: FFMA. */
 int tfcuda_matmul(uint64_t a, uint64_t b, uint64_t c, size_t batch, size_t m, size_t n, size_t k, int mode);
 
+/* C (MxN) = A^T @ B with A [RxM], B [RxN] row-major fp32, contracted over the leading extent R: the weight gradient of
+ * Y = X @ W (dW = X^T dY).  Replaces the reference VJP's batched Transpose(X)[b] @ dY[b] + batch reductions
+ * (Implementations.cpp:133-135, 560-646, 243-303) with one split-K pass; deterministic (fixed-order partial sums). */
+int tfcuda_matmul_tn(uint64_t a, uint64_t b, uint64_t c, size_t r, size_t m, size_t n);
+
 /* One all-pairs gravity step on N bodies, X,V: [N,3] fp32 (n-body-benchmark.py:16-34). */
 int tfcuda_nbody_step(uint64_t x, uint64_t v, uint64_t x_new, uint64_t v_new, size_t n, float dt, float eps);
 

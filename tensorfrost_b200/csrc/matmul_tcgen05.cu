@@ -438,8 +438,8 @@ int tfcuda_matmul_tcgen05(const float* a, const float* b, float* c, size_t batch
 	const size_t na = m * k, nb = k * n;
 	const size_t na4 = (na + 3) & ~size_t(3), nb4 = (nb + 3) & ~size_t(3);
 	// scratch planes: mode 0: [Bt]; mode 1: [A_hi | A_lo | Bt_hi | Bt_lo]
-	float* scratch = nullptr;
-	TFCUDA_CHECK(cudaMallocAsync(&scratch, (mode == 0 ? nb4 : 2 * na4 + 2 * nb4) * sizeof(float), s.stream));
+	float* scratch = static_cast<float*>(tfcuda::scratch((mode == 0 ? nb4 : 2 * na4 + 2 * nb4) * sizeof(float)));
+	if (!scratch) return 1;
 	const unsigned t_tiles = (unsigned)(((n + 31) / 32) * ((k + 31) / 32));
 	const unsigned t_grid = std::min<unsigned>(t_tiles, (unsigned)s.sm_count * 16);
 	int rc = 0;
@@ -478,6 +478,5 @@ int tfcuda_matmul_tcgen05(const float* a, const float* b, float* c, size_t batch
 			else rc = launch<32, true>(a_hi, bt_hi, a_lo, bt_lo, pc, m, n, k);
 		}
 	}
-	TFCUDA_CHECK(cudaFreeAsync(scratch, s.stream));
 	return rc;
 }

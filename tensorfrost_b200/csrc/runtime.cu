@@ -82,6 +82,32 @@ static size_t guard_bytes() {
 	return g;
 }
 
+static void* g_scratch = nullptr;
+static size_t g_scratch_bytes = 0;
+
+void* scratch(size_t bytes) {
+	if (bytes <= g_scratch_bytes) return g_scratch;
+	if (g_scratch) cudaFreeAsync(g_scratch, g_state.stream);
+	g_scratch = nullptr;
+	g_scratch_bytes = 0;
+	size_t want = (bytes + (bytes >> 3) + 0xfffff) & ~size_t(0xfffff);
+	void* p = nullptr;
+	cudaError_t e = cudaMallocAsync(&p, want, g_state.stream);
+	if (e != cudaSuccess) {
+		(void)cudaGetLastError();
+		want = bytes;
+		e = cudaMallocAsync(&p, want, g_state.stream);
+	}
+	if (e != cudaSuccess) {
+		set_error("tfcuda: scratch allocation of " + std::to_string(bytes) + " bytes failed: " + cuda_err(e));
+		(void)cudaGetLastError();
+		return nullptr;
+	}
+	g_scratch = p;
+	g_scratch_bytes = want;
+	return p;
+}
+
 static Buffer* create_buffer(size_t words) {
 	require_init();
 	if (words == 0) throw std::invalid_argument("tfcuda: trying to allocate a buffer with size 0");
@@ -447,6 +473,9 @@ int tfcuda_shutdown(void) {
 		for (Buffer* b : kv.second) destroy_buffer(b);
 	g_pool.free_lists.clear();
 	g_pool.unused_words = 0;
+	if (g_scratch) cudaFreeAsync(g_scratch, g_state.stream);
+	g_scratch = nullptr;
+	g_scratch_bytes = 0;
 	for (CUmodule m : g_modules) g_state.drv.ModuleUnload(m);
 	g_modules.clear();
 	g_kernels.clear();

@@ -52,6 +52,11 @@ inline uint64_t dptr_of(const TFBuffer* b) { return reinterpret_cast<const Buffe
 
 void require_init();  // throws std::runtime_error when tfcuda_init has not succeeded
 
+// Grow-only device scratch shared by the library kernels (matmul planes, split-K partials).  Everything runs on ONE stream, so
+// consecutive library calls can reuse the same block; keeping it avoids a multi-GB cudaMallocAsync/cudaFreeAsync pair per call
+// (150 per NCA training step).  Returns nullptr (error set) when the device cannot provide it.  Valid until the next call.
+void* scratch(size_t bytes);
+
 #define TFCUDA_CHECK(expr)                                                                   \
 	do {                                                                                     \
 		cudaError_t _e = (expr);                                                             \

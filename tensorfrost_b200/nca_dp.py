@@ -30,7 +30,7 @@ import time
 
 import numpy as np
 
-from . import workloads
+from . import REPO_ROOT, workloads
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -278,12 +278,19 @@ def bench_main(args):
         tf.cuda_synchronize()
         if dist is not None:
             dist.barrier()
+        sys.path.insert(0, REPO_ROOT)
+        from bench import ClockSampler  # nvidia-smi clocks / throttle reasons of THIS rank's GPU during the timed region
+        sampler = ClockSampler(local)
+        sampler.start()
         launches0 = tf.cuda_launch_count()
         tf.cuda_timer_begin()
+        host_t0 = time.perf_counter()
         for _ in range(args.steps):
             tr.step()
+        host_issue_ms = (time.perf_counter() - host_t0) * 1e3  # host time to ENQUEUE the steps (it runs ahead of the device)
         ms = tf.cuda_timer_end()
         tf.cuda_synchronize()
+        clocks = sampler.stop()
         launches = tf.cuda_launch_count() - launches0
         loss = tr.step(read_loss=True)
         top = None
@@ -296,6 +303,10 @@ def bench_main(args):
             total = sum(r["total_ms"] for r in recs)
             top = [{"name": r["name"], "launches": r["launches"], "ms": round(r["total_ms"], 3), "share": round(r["total_ms"] / total, 4),
                     "gbs": round(r["bytes"] / max(r["total_ms"], 1e-9) / 1e6, 1)} for r in recs[:24]]
+            dump = os.environ.get("TFCUDA_PROFILE_DUMP")
+            if dump:
+                with open(dump, "w") as f:
+                    json.dump(recs, f)
             top.append({"name": "TOTAL", "launches": sum(r["launches"] for r in recs), "ms": round(total, 3), "gb": round(sum(r["bytes"] for r in recs) / 1e9, 2)})
         if dist is not None:
             import torch
@@ -315,7 +326,8 @@ def bench_main(args):
                                    f"{args.nca_steps} CA steps, pool {args.nca_pool}", "parallelism": f"dp{world}",
                        "per_rank_batch": args.nca_batch // world, "exchange": "ncclAllReduce(sum) of 7821 fp32 + scale, once per step",
                        "program": "reference single program" if args.nca_mono else "grad program -> allreduce -> apply program"},
-            "gpu_launches": int(launches), "loss_after": loss, "build_seconds": build_s,
+            "gpu_launches": int(launches), "loss_after": loss, "build_seconds": build_s, "clocks": clocks,
+            "host_issue_ms_per_step": host_issue_ms / args.steps,
         }
         if top is not None:
             line["top_kernels"] = top

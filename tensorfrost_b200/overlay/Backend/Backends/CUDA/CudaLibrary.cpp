@@ -41,11 +41,13 @@ using namespace tfcuda_abi;
 namespace TensorFrost {
 
 extern map<string, ImplementationFunction> implementation_functions;  // Compiler/Implementations.cpp:648
+extern map<string, VJPGradientFunction> gradient_functions;           // Compiler/Implementations.cpp:86
 
 namespace {
 
 const char* const kMarker = "tfcuda_lib:";
 map<string, ImplementationFunction> g_generic;        // the reference's own lowerings, kept for the cases the library declines
+VJPGradientFunction g_generic_matmul_vjp;             // the reference's matmul VJP (Implementations.cpp:133-135)
 unordered_map<size_t, CudaLibraryCall> g_calls;       // kernel id -> library call (filled by the emitter)
 bool g_installed = false;
 
@@ -154,6 +156,22 @@ void LowerPrefixSum(Tensors& outputs, map<int, const Tensor*> inputs, const Tens
 	outputs.push_back(result);
 }
 
+// Is `t` the lowered form of a plain 2-D transpose (ComputeTranspose, Implementations.cpp:455-489: an Unsafe load of the source
+// with the two dim_id indices swapped)?  Returns the source tensor S (t = S^T) or nullptr.
+const Tensor* TransposedSource(const Tensor* t) {
+	Node* node = t->node_;
+	if (node->name != "load" || t->GetDimension() != 2) return nullptr;
+	if (!node->args.Has(ArgType::Memory) || !node->args.Has(ArgType::Index, 0) || !node->args.Has(ArgType::Index, 1)) return nullptr;
+	if (node->args.Has(ArgType::Index, 2)) return nullptr;
+	const Tensor* source = node->args.Get(ArgType::Memory)->GetTensor();
+	if (source->GetDimension() != 2) return nullptr;
+	Node* i0 = node->args.Get(ArgType::Index, 0);
+	Node* i1 = node->args.Get(ArgType::Index, 1);
+	if (i0->name != "dim_id" || i1->name != "dim_id") return nullptr;
+	if ((int)i0->data[0] != 1 || (int)i1->data[0] != 0) return nullptr;
+	return source;
+}
+
 // matmul: A [.., M, K] @ B [K, N] (B 2-D: the leading dims of A fold into M) or equal-rank batched operands; fp32 only.
 void LowerMatmul(Tensors& outputs, map<int, const Tensor*> inputs, const Tensor* tensor, vector<int> axes) {
 	const Tensor* a = inputs[0];
@@ -168,11 +186,51 @@ void LowerMatmul(Tensors& outputs, map<int, const Tensor*> inputs, const Tensor*
 		return;
 	}
 	Tensors out_shape = tensor->GetShape();
+	// S^T @ B with 2-D S [R, M] and B [R, N] (what CudaMatmulVJP emits for weight gradients, or a user's `x.T @ y`): contracted over
+	// the leading extent of both operands as they lie in memory, no transposed copy (tfcuda_matmul_tn)
+	if (da == 2 && EnvInt("TFCUDA_LIBRARY_MATMUL_TN", 1) != 0) {
+		if (const Tensor* source = TransposedSource(a)) {
+			vector<Tensor*> bufs = EmitLibraryCall(string(kMarker) + "matmul_tn", {source, b}, {{out_shape, tensor->node_->format}});
+			Tensor* result = ElementView(bufs[0], out_shape);
+			result->SetDebugName("matmul_tn");
+			outputs.push_back(result);
+			return;
+		}
+	}
 	int mode = EnvInt("TFCUDA_MATMUL_MODE", 1);  // 1 = 3xTF32 (fp32-accurate) by default; 0 = single TF32; 2 = FFMA
 	vector<Tensor*> bufs = EmitLibraryCall(string(kMarker) + "matmul:" + to_string(mode), {a, b}, {{out_shape, tensor->node_->format}});
 	Tensor* result = ElementView(bufs[0], out_shape);
 	result->SetDebugName("matmul");
 	outputs.push_back(result);
+}
+
+// VJP of C = A @ B on this backend.  dA = dC @ B^T as in the reference (Implementations.cpp:133-135).  For a 2-D B (a weight matrix
+// applied to every row of an N-D A) the reference forms dB = Transpose(A)[batch] @ dC[batch] per leading slice and lets
+// ReduceGradientToShape sum the [batch.., K, N] products over the batch axes (:5-54).  The same value is ONE contraction over all rows:
+// dB = A2^T @ dC2 with A2 = A viewed as [rows, K] and dC2 = dC viewed as [rows, N]; LowerMatmul sends it to tfcuda_matmul_tn.
+void CudaMatmulVJP(ArgumentManager& in, const Tensor& out, const Tensor& grad, NodeGrads& grads) {
+	const Tensor& a = in[0];
+	const Tensor& b = in[1];
+	bool fold = LibraryEnabled() && EnvInt("TFCUDA_LIBRARY_MATMUL", 1) != 0 && EnvInt("TFCUDA_LIBRARY_MATMUL_TN", 1) != 0 &&
+	            b.GetDimension() == 2 && a.GetDimension() > 2 && a.node_->format.type == TFType::Float && b.node_->format.type == TFType::Float;
+	if (!fold) {
+		g_generic_matmul_vjp(in, out, grad, grads);
+		return;
+	}
+	// internal shapes are innermost-first: A = [K, M, batch...], dC = [N, M, batch...]
+	Tensors sa = a.GetShape();
+	Tensors sg = grad.GetShape();
+	const Tensor* rows = sa[1];
+	long long const_rows = sa[1]->TryGetConstant();
+	for (size_t i = 2; i < sa.size(); i++) {
+		int c = sa[i]->TryGetConstant();
+		const_rows = (const_rows >= 0 && c >= 0) ? const_rows * c : -1;
+		rows = &(*rows * *sa[i]);
+	}
+	if (const_rows >= 0 && const_rows < 0x7fffffffLL) rows = &Tensor::Constant((int)const_rows);
+	Tensor& a2 = Tensor::Reshape(a, {sa[0], rows});
+	Tensor& g2 = Tensor::Reshape(grad, {sg[0], rows});
+	grads.Add(Tensor::Matmul(grad, Tensor::Transpose(b)), Tensor::Matmul(Tensor::Transpose(a2), g2));
 }
 
 size_t Extent(const TFTensor& t, size_t from, size_t to) {
@@ -206,6 +264,8 @@ void InstallCudaLibraryLowerings() {
 	implementation_functions["dim_prefix_sum"] = LowerPrefixSum;
 	g_generic["matmul"] = implementation_functions.at("matmul");
 	implementation_functions["matmul"] = LowerMatmul;
+	g_generic_matmul_vjp = gradient_functions.at("matmul");
+	gradient_functions["matmul"] = CudaMatmulVJP;
 	g_installed = true;
 }
 
@@ -297,6 +357,17 @@ void DispatchCudaLibraryCall(const CudaLibraryCall& call, const TFDispatchInfo& 
 		}
 		if (batch * m * n == 0) return;
 		Check(tfcuda_matmul(Ptr(a), Ptr(b), Ptr(c), batch, m, n, k, call.params[0]), "matmul");
+	} else if (call.op == "matmul_tn") {
+		need(2, 1, 0);
+		const TFTensor& a = tensor(call.inputs[0]);  // [R, M] (possibly a reshaped view of an N-D tensor)
+		const TFTensor& b = tensor(call.inputs[1]);  // [R, N]
+		const TFTensor& c = tensor(call.outputs[0]);
+		size_t m = a.shape[a.dim - 1], n = b.shape[b.dim - 1];
+		size_t r = Extent(a, 0, a.dim - 1);
+		if (Extent(b, 0, b.dim - 1) != r) throw std::runtime_error("CUDA backend: matmul_tn operands have different row counts at run time");
+		if (Extent(c, 0, c.dim) != m * n) throw std::runtime_error("CUDA backend: matmul_tn output extent mismatch");
+		if (m * n == 0) return;
+		Check(tfcuda_matmul_tn(Ptr(a), Ptr(b), Ptr(c), r, m, n), "matmul_tn");
 	} else if (call.op == "sort") {
 		bool has_values = call.params.size() > 0 && call.params[0] != 0;
 		need(has_values ? 2 : 1, has_values ? 2 : 1, 2);

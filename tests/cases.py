@@ -561,6 +561,42 @@ def _autograd():
     return build, make_inputs
 
 
+@case("autograd_batched_dense", tol=1e-4, default_size=6)
+def _autograd_batched_dense():
+    """Two dense layers applied to every cell of a [n, h, w, c] field (the NCA layer shape, nca.py:50-56) and the gradients of
+    both weight matrices and biases: the matmul VJP with an N-D left operand and a 2-D weight (Implementations.cpp:133-135).
+    Also a direct `x2.T @ y2` over the flattened rows."""
+    def build(tf):
+        cin, hidden, cout, h, w = 8, 32, 12, 10, 7
+
+        def prog():
+            x = tf.input([-1, h, w, cin], tf.float32)
+            n = x.shape[0]
+            w1 = tf.input([cin, hidden], tf.float32)
+            b1 = tf.input([hidden], tf.float32)
+            w2 = tf.input([hidden, cout], tf.float32)
+            b2 = tf.input([cout], tf.float32)
+            t = tf.input([n, h, w, cout], tf.float32)
+            a = x @ w1 + b1
+            a = tf.select(a > 0.0, a, 0.01 * a)
+            y = a @ w2 + b2
+            loss = tf.mean(tf.mean(tf.mean(tf.mean((y - t) ** 2.0))))
+            grads = [tf.grad(loss, p) for p in (w1, b1, w2, b2)]
+            rows = n * (h * w)
+            x2 = tf.reshape(x, [rows, cin])
+            t2 = tf.reshape(t, [rows, cout])
+            return [loss, y] + grads + [x2.T @ t2]
+        return tf.compile(prog)
+
+    def make_inputs(rng, size):
+        cin, hidden, cout, h, w = 8, 32, 12, 10, 7
+        return [rng.standard_normal((size, h, w, cin)).astype(np.float32),
+                (0.3 * rng.standard_normal((cin, hidden))).astype(np.float32), (0.1 * rng.standard_normal(hidden)).astype(np.float32),
+                (0.3 * rng.standard_normal((hidden, cout))).astype(np.float32), (0.1 * rng.standard_normal(cout)).astype(np.float32),
+                rng.standard_normal((size, h, w, cout)).astype(np.float32)]
+    return build, make_inputs
+
+
 # ---------------------------------------------------------------------------------------------
 def run_case(tf, name, seed=0, size=None, program=None):
     """Build (or reuse) the program of a case, run it on seeded inputs, return (outputs as numpy, program)."""

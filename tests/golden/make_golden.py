@@ -25,6 +25,7 @@ GOLDEN = {
     "split_merge": (128, 0), "sort_radix_u32": (1 << 14, 0), "sort_radix_f32": (1 << 14, 0), "sort_radix_i32": (1 << 14, 0),
     "sort_bitonic_u32": (1 << 12, 0), "atomics": (20000, 0), "scatter_matmul": (48, 0), "matmul": (160, 0), "qr_inverse": (5, 0),
     "nbody": (512, 0), "nbody_loop": (512, 0), "host_loop": (200, 0), "autograd_mlp": (32, 0),
+    "autograd_batched_dense": (6, 0),
 }
 
 

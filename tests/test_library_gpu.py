@@ -220,6 +220,24 @@ def test_matmul_tcgen05_batched_and_unaligned_fallback(tfcuda_lib):
     assert rel_err(d_c.get(), tf_oracle.matmul(a, b)) <= 1e-6
 
 
+@pytest.mark.parametrize("r,m,n", [(1, 1, 1), (5, 3, 2), (4097, 48, 128), (10000, 128, 12), (3000, 130, 70), (777, 20, 24), (100000, 48, 128), (65536, 128, 12)])
+def test_matmul_tn(tfcuda_lib, r, m, n):
+    """C = A^T @ B contracted over the leading extent (the weight-gradient kernel).  fp32 FFMA products, split-K partial sums added
+    in a fixed order: 2e-6 of the result scale against float64 (far inside north_star's 1e-3 matmul/gradient bar), and bit-identical
+    between two runs (no float atomics)."""
+    rng = np.random.default_rng(r + m + n)
+    a, b = rng.standard_normal((r, m)).astype(np.float32), rng.standard_normal((r, n)).astype(np.float32)
+    d_a, d_b = abi.DeviceArray(a), abi.DeviceArray(b)
+    d_c, d_c2 = abi.DeviceArray(np.full((m, n), np.nan, np.float32)), abi.DeviceArray(np.full((m, n), np.nan, np.float32))
+    abi.check(tfcuda_lib.tfcuda_matmul_tn(d_a.ptr, d_b.ptr, d_c.ptr, r, m, n), "matmul_tn")
+    abi.check(tfcuda_lib.tfcuda_matmul_tn(d_a.ptr, d_b.ptr, d_c2.ptr, r, m, n), "matmul_tn")
+    want = a.astype(np.float64).T @ b.astype(np.float64)
+    got = d_c.get()
+    assert rel_err(got, want) <= 2e-6
+    assert np.array_equal(got.view(np.uint32), d_c2.get().view(np.uint32))
+    assert rel_err(got, tf_oracle.matmul(np.ascontiguousarray(a.T), b)) <= 1e-5 if r <= 10000 else True
+
+
 # ---- n-body --------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n", [1, 2, 255, 256, 257, 1500])
 def test_nbody_step(tfcuda_lib, n):
