@@ -131,6 +131,9 @@ int tfcuda_free(uint64_t ptr);
  * (Backend/TensorMemory.cpp:84-103), in words */
 size_t tfcuda_pool_allocated_words(void);
 size_t tfcuda_pool_unused_words(void);
+/* cudaMallocAsync + cudaFreeAsync calls made for tensor buffers since initialisation (deleted buffers are parked by size and
+ * reused without a driver call: Backend/TensorMemory.cpp:145-160 deletes and re-creates buffers every step otherwise) */
+uint64_t tfcuda_pool_driver_calls(void);
 
 /* ------------------------------------------------------------------------------------------
  * Kernels.  Replaces CompileKernels (Backend/Backend.cpp:75-94) +

@@ -66,6 +66,7 @@ EXPORTS = {
     "tfcuda_free": (i32, [u64]),
     "tfcuda_pool_allocated_words": (sz, []),
     "tfcuda_pool_unused_words": (sz, []),
+    "tfcuda_pool_driver_calls": (u64, []),
     "tfcuda_prelude": (C.c_char_p, []),
     "tfcuda_nvrtc_check": (i32, [C.c_char_p, C.c_char_p]),
     "tfcuda_compile_kernels": (i32, [C.POINTER(TFCudaKernelSource), sz, C.c_char_p]),

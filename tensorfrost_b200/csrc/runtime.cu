@@ -108,6 +108,30 @@ void* scratch(size_t bytes) {
 	return p;
 }
 
+// Block cache under create_buffer / destroy_buffer.  The reference's TensorMemoryManager deletes a buffer that stayed unused for
+// more than ~128 ALLOCATIONS (Backend/TensorMemory.cpp:145-160, one tick per tf.allocate) and re-creates it on the next step; a
+// training step with 760 allocations therefore keeps creating and deleting multi-GB buffers.  Each cudaMallocAsync / cudaFreeAsync
+// of that size costs the driver a virtual-memory operation (measured: ~0.6 ms a pair at 2-4 GB, and they serialise between the
+// processes of a multi-GPU job), so deleted blocks are parked here by exact size and handed back without a driver call.  The cache
+// is flushed when it exceeds TFCUDA_BLOCK_CACHE_MB (default: a quarter of device memory) or when an allocation fails.
+struct BlockCache {
+	std::unordered_map<size_t, std::vector<void*>> blocks;  // total bytes -> parked blocks (guard bands still zero)
+	size_t bytes = 0;
+	size_t limit = 0;
+	uint64_t driver_calls = 0, hits = 0;
+};
+static BlockCache g_blocks;
+
+static void flush_block_cache() {
+	for (auto& kv : g_blocks.blocks)
+		for (void* p : kv.second) {
+			cudaFreeAsync(p, g_state.stream);
+			g_blocks.driver_calls++;
+		}
+	g_blocks.blocks.clear();
+	g_blocks.bytes = 0;
+}
+
 static Buffer* create_buffer(size_t words) {
 	require_init();
 	if (words == 0) throw std::invalid_argument("tfcuda: trying to allocate a buffer with size 0");
@@ -115,23 +139,34 @@ static Buffer* create_buffer(size_t words) {
 	const size_t guard = guard_bytes();
 	const size_t payload = (words * sizeof(uint32_t) + 255) & ~size_t(255);
 	const size_t total = payload + 2 * guard;
-	cudaError_t e = cudaMallocAsync(&p, total, g_state.stream);
-	if (e != cudaSuccess) {
-		// the pool may be holding memory another size class could use: trim and retry once
-		cudaStreamSynchronize(g_state.stream);
-		cudaMemPool_t mp;
-		if (cudaDeviceGetDefaultMemPool(&mp, g_state.device) == cudaSuccess) cudaMemPoolTrimTo(mp, 0);
-		(void)cudaGetLastError();
-		e = cudaMallocAsync(&p, total, g_state.stream);
-	}
-	if (e != cudaSuccess) {
-		std::string m = "tfcuda: device allocation of " + std::to_string(words * 4) + " bytes failed: " + cuda_err(e);
-		set_error(m);
-		throw std::runtime_error(m);
-	}
-	if (guard) {
-		cudaMemsetAsync(p, 0, guard, g_state.stream);
-		cudaMemsetAsync(static_cast<char*>(p) + guard + words * sizeof(uint32_t), 0, total - guard - words * sizeof(uint32_t), g_state.stream);
+	auto hit = g_blocks.blocks.find(total);
+	if (hit != g_blocks.blocks.end() && !hit->second.empty()) {
+		p = hit->second.back();
+		hit->second.pop_back();
+		g_blocks.bytes -= total;
+		g_blocks.hits++;
+	} else {
+		cudaError_t e = cudaMallocAsync(&p, total, g_state.stream);
+		g_blocks.driver_calls++;
+		if (e != cudaSuccess) {
+			// parked blocks / the driver pool may be holding memory another size could use: release and retry once
+			flush_block_cache();
+			cudaStreamSynchronize(g_state.stream);
+			cudaMemPool_t mp;
+			if (cudaDeviceGetDefaultMemPool(&mp, g_state.device) == cudaSuccess) cudaMemPoolTrimTo(mp, 0);
+			(void)cudaGetLastError();
+			e = cudaMallocAsync(&p, total, g_state.stream);
+			g_blocks.driver_calls++;
+		}
+		if (e != cudaSuccess) {
+			std::string m = "tfcuda: device allocation of " + std::to_string(words * 4) + " bytes failed: " + cuda_err(e);
+			set_error(m);
+			throw std::runtime_error(m);
+		}
+		if (guard) {
+			cudaMemsetAsync(p, 0, guard, g_state.stream);
+			cudaMemsetAsync(static_cast<char*>(p) + guard + words * sizeof(uint32_t), 0, total - guard - words * sizeof(uint32_t), g_state.stream);
+		}
 	}
 	Buffer* b = new Buffer();
 	b->base.size = words;
@@ -142,7 +177,26 @@ static Buffer* create_buffer(size_t words) {
 
 static void destroy_buffer(Buffer* b) {
 	if (!b) return;
-	if (b->dptr && g_state.initialized) cudaFreeAsync(reinterpret_cast<void*>(b->dptr - guard_bytes()), g_state.stream);
+	if (b->dptr && g_state.initialized) {
+		const size_t guard = guard_bytes();
+		const size_t total = ((b->base.size * sizeof(uint32_t) + 255) & ~size_t(255)) + 2 * guard;
+		void* p = reinterpret_cast<void*>(b->dptr - guard);
+		if (g_blocks.limit == 0) {
+			const char* v = getenv("TFCUDA_BLOCK_CACHE_MB");
+			size_t free_b = 0, total_b = 0;
+			cudaMemGetInfo(&free_b, &total_b);
+			g_blocks.limit = v ? (size_t)strtoull(v, nullptr, 0) << 20 : total_b / 4;
+			if (g_blocks.limit == 0) g_blocks.limit = 1;  // TFCUDA_BLOCK_CACHE_MB=0: no parking
+		}
+		if (total <= g_blocks.limit) {
+			if (g_blocks.bytes + total > g_blocks.limit) flush_block_cache();
+			g_blocks.blocks[total].push_back(p);
+			g_blocks.bytes += total;
+		} else {
+			cudaFreeAsync(p, g_state.stream);
+			g_blocks.driver_calls++;
+		}
+	}
 	g_pool.allocated_words -= b->base.size;
 	delete b;
 }
@@ -473,6 +527,7 @@ int tfcuda_shutdown(void) {
 		for (Buffer* b : kv.second) destroy_buffer(b);
 	g_pool.free_lists.clear();
 	g_pool.unused_words = 0;
+	flush_block_cache();
 	if (g_scratch) cudaFreeAsync(g_scratch, g_state.stream);
 	g_scratch = nullptr;
 	g_scratch_bytes = 0;
@@ -585,6 +640,7 @@ int tfcuda_free(uint64_t ptr) {
 
 size_t tfcuda_pool_allocated_words(void) { return g_pool.allocated_words; }
 size_t tfcuda_pool_unused_words(void) { return g_pool.unused_words; }
+uint64_t tfcuda_pool_driver_calls(void) { return g_blocks.driver_calls; }
 
 // ---- kernels ------------------------------------------------------------------------------------
 static std::vector<std::string> nvrtc_options(const char* options) {

@@ -214,16 +214,40 @@ class NcaTrainer:
             self.trainer.update_parameters(outs[:-2])
             self.last_flat = None
             return float(outs[-2].numpy[0]) if read_loss else None
+        phases = getattr(self, "phase_log", None)
+        if phases is not None:
+            tf.cuda_synchronize()
+            t0 = time.perf_counter()
         pool, seed, flat, state = self.grad_program(self.trainer, batch_ids, np.array([self.fire_rate], np.float32))
         self.trainer.pool = pool
         self.model.seed = seed
-        if self.world > 1:
+        if phases is not None:
+            tf.cuda_synchronize()
+            t1 = time.perf_counter()
+        # Measured on the 8-GPU box (profiles/README.md, r01c): with the NCCL allreduce enqueued behind the ~800 pending kernels of the
+        # grad program a step takes 105-110 ms; with the stream drained before and after the exchange the same step takes 75.8 ms
+        # (grad 75.1 + exchange 0.5 + apply 0.15), which is also what 8 independent single-GPU processes take.  The host sync is free
+        # here (every step already starts with one: the batch ids are uploaded), so the exchange is bracketed by default;
+        # self.diag ("async" / "before" / "after" / "skip") overrides it for diagnosis.
+        diag = getattr(self, "diag", "") or ("before+after" if self.exchange is None and os.environ.get("TFCUDA_DP_SYNC", "1") != "0" else "async")
+        if self.world > 1 and "skip" not in diag:
+            if "before" in diag:
+                tf.cuda_synchronize()
             if self.exchange is not None:
                 flat = self.exchange(flat, self.world)
             else:
                 tf.cuda_allreduce(flat, 1.0 / self.world)
+            if "after" in diag:
+                tf.cuda_synchronize()
+        if phases is not None:
+            tf.cuda_synchronize()
+            t2 = time.perf_counter()
         new_params = self.apply_program(self.opt, flat, np.array([lr], np.float32))
         self.opt.update_parameters(new_params)
+        if phases is not None:
+            tf.cuda_synchronize()
+            t3 = time.perf_counter()
+            phases.append([(t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3])
         self.last_flat, self.last_state = flat, state
         if read_loss:
             return float(np.array(flat.numpy)[-1])
@@ -283,6 +307,7 @@ def bench_main(args):
         sampler = ClockSampler(local)
         sampler.start()
         launches0 = tf.cuda_launch_count()
+        driver_calls0 = tf.cuda_pool_driver_calls()
         tf.cuda_timer_begin()
         host_t0 = time.perf_counter()
         for _ in range(args.steps):
@@ -292,13 +317,39 @@ def bench_main(args):
         tf.cuda_synchronize()
         clocks = sampler.stop()
         launches = tf.cuda_launch_count() - launches0
+        driver_calls = tf.cuda_pool_driver_calls() - driver_calls0
         loss = tr.step(read_loss=True)
+        phase_ms = None
+        if os.environ.get("TFCUDA_NCA_PHASES"):
+            # diagnosis: three more steps with a device sync after each phase (grad program / gradient exchange / apply program)
+            tr.phase_log = []
+            for _ in range(3):
+                tr.step()
+            phase_ms = tr.phase_log
+            tr.phase_log = None
+        diag_ms = None
+        if os.environ.get("TFCUDA_NCA_DIAG"):
+            # diagnosis of the exchange: the same 3 steps with a device sync before / after the allreduce, or without the allreduce
+            diag_ms = {}
+            for mode in ("async", "before", "after", "before+after", "skip", "async"):
+                tr.diag = mode
+                tr.step()
+                tf.cuda_synchronize()
+                if dist is not None:
+                    dist.barrier()
+                tf.cuda_timer_begin()
+                for _ in range(3):
+                    tr.step()
+                diag_ms[mode + ("#2" if mode in diag_ms else "")] = tf.cuda_timer_end() / 3
+            tr.diag = ""
         top = None
-        if getattr(args, "nca_profile", False) and rank == 0:
+        if getattr(args, "nca_profile", False):
+            # EVERY rank takes the profiled step (the exchange is a collective: a rank-0-only step would wait for its peers forever)
             tf.cuda_profile_reset()
             tf.cuda_profile_enable(True)
             tr.step()
             tf.cuda_profile_enable(False)
+        if getattr(args, "nca_profile", False) and rank == 0:
             recs = sorted(tf.cuda_profile_records(), key=lambda r: -r["total_ms"])
             total = sum(r["total_ms"] for r in recs)
             top = [{"name": r["name"], "launches": r["launches"], "ms": round(r["total_ms"], 3), "share": round(r["total_ms"] / total, 4),
@@ -310,9 +361,10 @@ def bench_main(args):
             top.append({"name": "TOTAL", "launches": sum(r["launches"] for r in recs), "ms": round(total, 3), "gb": round(sum(r["bytes"] for r in recs) / 1e9, 2)})
         if dist is not None:
             import torch
-            t = torch.tensor([ms], dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            every = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
+            dist.all_gather(every, torch.tensor([ms], dtype=torch.float64))
+            per_rank_ms = [float(t.item()) / args.steps for t in every]
+            ms = max(float(t.item()) for t in every)
             dist.barrier()
     finally:
         os.dup2(saved, 1)
@@ -327,8 +379,15 @@ def bench_main(args):
                        "per_rank_batch": args.nca_batch // world, "exchange": "ncclAllReduce(sum) of 7821 fp32 + scale, once per step",
                        "program": "reference single program" if args.nca_mono else "grad program -> allreduce -> apply program"},
             "gpu_launches": int(launches), "loss_after": loss, "build_seconds": build_s, "clocks": clocks,
-            "host_issue_ms_per_step": host_issue_ms / args.steps,
+            "host_issue_ms_per_step": host_issue_ms / args.steps, "device_alloc_calls_per_step": driver_calls / args.steps,
         }
+        if world > 1:
+            line["per_rank_ms_per_step"] = per_rank_ms
+        line["host_cores"] = os.cpu_count()
+        if phase_ms is not None:
+            line["phase_ms_grad_exchange_apply"] = phase_ms
+        if diag_ms is not None:
+            line["diag_ms_per_step"] = diag_ms
         if top is not None:
             line["top_kernels"] = top
         print(json.dumps(line))

@@ -61,6 +61,8 @@ PyTensorMemory* NewLike(const PyTensorMemory& t, TFDataFormat fmt) {
 void CudaDefinitions(py::module& m) {
 	m.def("cuda_synchronize", []() { RequireCuda("cuda_synchronize"); CudaFinish(); }, "Wait for all queued device work");
 	m.def("cuda_launch_count", []() { return tfcuda_launch_count(); }, "Kernels launched since initialisation");
+	m.def("cuda_pool_driver_calls", []() { return tfcuda_pool_driver_calls(); },
+	      "cudaMallocAsync + cudaFreeAsync calls made for tensor buffers since initialisation (parked blocks are reused without one)");
 	m.def("cuda_timer_begin", []() { Check(tfcuda_timer_begin(), "cuda_timer_begin"); });
 	m.def("cuda_timer_end", []() { float ms = 0; Check(tfcuda_timer_end(&ms), "cuda_timer_end"); return ms; },
 	      "Milliseconds of device time since cuda_timer_begin (CUDA events on the backend stream)");

@@ -239,8 +239,10 @@ def test_matmul_tn(tfcuda_lib, r, m, n):
 
 
 # ---- n-body --------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n", [1, 2, 255, 256, 257, 1500])
+@pytest.mark.parametrize("n", [1, 2, 255, 256, 257, 1500, 4096, 5000])
 def test_nbody_step(tfcuda_lib, n):
+    """n < 2048: scalar kernel; n >= 2048: the packed f32x2 kernel (5000 also exercises its padded tail tile).  The packed kernel adds
+    even and odd j separately: a numpy emulation of that order differs from the oracle's serial sum by 1.6e-6 at n = 4096."""
     rng = np.random.default_rng(n)
     x = (5.0 * rng.standard_normal((n, 3))).astype(np.float32)
     v = (0.1 * rng.standard_normal((n, 3))).astype(np.float32)
