@@ -170,6 +170,44 @@ def barrier(dist, tf):
         torch.cuda.synchronize()
 
 
+def ncu_traffic(kernel_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of an emitted fluid kernel, from the committed `ncu --set full` capture
+    of this same command (profiles/README.md); None when the capture does not hold that kernel."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r01b_fluid_ncu_full_summary.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        col = {h: i for i, h in enumerate(rows[0])}
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        vals = []
+        for r in rows[2:]:
+            if r[col["Kernel Name"]] == kernel_name:
+                rd = float(r[col["dram__bytes_read.sum"]]) * unit[rows[1][col["dram__bytes_read.sum"]]]
+                wr = float(r[col["dram__bytes_write.sum"]]) * unit[rows[1][col["dram__bytes_write.sum"]]]
+                vals.append(rd + wr)
+        return sum(vals) / len(vals) if vals else None
+    except (OSError, KeyError, ValueError, IndexError):
+        return None
+
+
+def ncu_limiter(kernel_name):
+    """What the same capture says limits that kernel: issue-slot, DRAM and L1 utilisation (percent of peak)."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r01b_fluid_ncu_full_summary.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        col = {h: i for i, h in enumerate(rows[0])}
+        for r in rows[2:]:
+            if r[col["Kernel Name"]] == kernel_name:
+                return {"issue_active_pct": float(r[col["smsp__issue_active.avg.pct_of_peak_sustained_active"]]),
+                        "dram_pct": float(r[col["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]]),
+                        "l1tex_pct": float(r[col["l1tex__throughput.avg.pct_of_peak_sustained_elapsed"]]),
+                        "warp_instructions": float(r[col["smsp__inst_executed.sum"]])}
+    except (OSError, KeyError, ValueError, IndexError):
+        pass
+    return None
+
+
 def dominant(records, steps):
     """Pick the kernel with the largest share of device time; return its roofline fields."""
     total = sum(r["total_ms"] for r in records) or 1.0
@@ -213,7 +251,8 @@ def bench_fluid(tf, dist, rank, world, args, peaks):
     value = world * step_bytes * args.steps / (ms / 1e3) / 1e9
     achieved = top_bytes / (top_ms / 1e3) / 1e9 if top_ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "traffic": None, "kernel": top["name"], "share_of_step": share, "launch_ms": top_ms, "algorithmic_bytes_per_launch": top_bytes,
+                "traffic": ncu_traffic(top["name"]) if n == 2048 else None, "traffic_source": "profiles/r01b_fluid_ncu_full_summary.csv (ncu --set full, same command)",
+                "kernel": top["name"], "ncu": ncu_limiter(top["name"]) if n == 2048 else None, "share_of_step": share, "launch_ms": top_ms, "algorithmic_bytes_per_launch": top_bytes,
                 "peak_source": peaks["source"],
                 "whole_step": {"achieved": step_bytes / (sum(r["total_ms"] for r in records) / args.steps / 1e3) / 1e9,
                                "note": "sum of algorithmic bytes / sum of kernel times over all 43 dispatches"}}
@@ -222,19 +261,31 @@ def bench_fluid(tf, dist, rank, world, args, peaks):
     for p, a in zip(pinned, host_inputs[:4]):
         p[...] = a
     e2e_state = [tf.cuda_tensor(a) for a in host_inputs]
+    direct = hasattr(tf, "cuda_download")
+    if direct:
+        try:
+            tf.cuda_download(e2e_state[0], pinned[0])
+            pinned[0][...] = host_inputs[0]
+        except Exception:  # noqa: BLE001 - older module: stage through tf.cuda_numpy
+            direct = False
     barrier(dist, tf)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         for k in range(4):
             tf.cuda_upload(e2e_state[k], pinned[k])
         e2e_state, _ = workloads.fluid_step(fluid, e2e_state)
-        outs = [tf.cuda_numpy(e2e_state[k]) for k in range(4)]
-        for p, o in zip(pinned, outs):
-            p[...] = o
+        if direct:
+            for k in range(4):
+                tf.cuda_download(e2e_state[k], pinned[k])  # device -> the same page-locked arrays, no pageable staging copy
+        else:
+            outs = [tf.cuda_numpy(e2e_state[k]) for k in range(4)]
+            for p, o in zip(pinned, outs):
+                p[...] = o
     tf.cuda_synchronize()
     e2e_s = max_over_ranks(dist, time.perf_counter() - t0)
     e2e = {"value": world * step_bytes * args.steps / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": 4 * n * n * 4,
-           "d2h_bytes_per_step": 4 * n * n * 4, "ms_per_step": e2e_s / args.steps * 1e3}
+           "d2h_bytes_per_step": 4 * n * n * 4, "ms_per_step": e2e_s / args.steps * 1e3,
+           "path": "pinned host arrays <-> device, tf.cuda_upload / " + ("tf.cuda_download" if direct else "tf.cuda_numpy + host copy")}
     return {"value": value, "ms": ms, "launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e, "step_bytes": step_bytes,
             "records": sorted(records, key=lambda r: -r["total_ms"])[:16]}
 

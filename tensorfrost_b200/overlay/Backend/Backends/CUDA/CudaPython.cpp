@@ -3,7 +3,7 @@
 //
 // Nothing here changes an existing tf.* function.  It adds what a device backend needs next to them:
 //   tf.cuda_synchronize / cuda_timer_* / cuda_launch_count   — device-side timing for benchmarks
-//   tf.cuda_tensor(np) / tf.cuda_numpy(t) / tf.cuda_upload   — bulk host<->device copies that skip the
+//   tf.cuda_tensor(np) / tf.cuda_numpy(t) / tf.cuda_upload / tf.cuda_download — bulk host<->device copies that skip the
 //        per-element std::function conversion of PyTensorMemory (Frontend/Python/PyTensorMemory.cpp:19-84,
 //        PyTensorMemory.h:30-45); same dtype rules for the 4-byte types, same result objects
 //   tf.cuda_device_ptr(t)                                     — interop (e.g. torch via __cuda_array_interface__)
@@ -120,6 +120,15 @@ void CudaDefinitions(py::module& m) {
 		if ((size_t)info.size != GetSize(t.tensor_)) throw std::runtime_error("cuda_upload: element count mismatch");
 		Check(tfcuda_memcpy_h2d(DevPtr(t), info.ptr, (size_t)info.size * 4), "cuda_upload");
 	}, "Overwrite an existing TensorMemory from a numpy array of the same size");
+
+	m.def("cuda_download", [](const PyTensorMemory& t, py::array arr) {
+		RequireCuda("cuda_download");
+		py::buffer_info info = arr.request(true);  // writable
+		(void)FormatOf(info);
+		if (!(arr.flags() & py::array::c_style)) throw std::runtime_error("cuda_download: the destination array must be C-contiguous");
+		if ((size_t)info.size != GetSize(t.tensor_)) throw std::runtime_error("cuda_download: element count mismatch");
+		Check(tfcuda_memcpy_d2h(info.ptr, DevPtr(t), (size_t)info.size * 4), "cuda_download");
+	}, "Copy a TensorMemory into an existing numpy array of the same size (a tf.cuda_pinned_array destination runs at full PCIe rate)");
 
 	m.def("cuda_numpy", [](const PyTensorMemory& t) -> py::array {
 		RequireCuda("cuda_numpy");
