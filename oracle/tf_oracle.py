@@ -145,6 +145,23 @@ def matmul(a, b):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# weight gradient of C = A @ B for a 2-D B and an N-D A — the matmul VJP, Compiler/Implementations.cpp:133-135:
+#   dB = Matmul(Transpose(A), dC) evaluated per leading slice (ComputeMatMul :560-646, serial k loop), then summed over the
+#   leading axes one at a time, outermost first (ReduceGradientToShape :5-54 -> ComputeReduction :243-303, serial loops).
+# ---------------------------------------------------------------------------------------------------------------
+def matmul_weight_grad(a, dc):
+    a = np.asarray(a, dtype=np.float32)
+    dc = np.asarray(dc, dtype=np.float32)
+    per_slice = matmul(np.swapaxes(a, -1, -2), dc)  # [batch..., K, N]
+    while per_slice.ndim > 2:
+        acc = np.zeros(per_slice.shape[1:], dtype=np.float32)
+        for i in range(per_slice.shape[0]):
+            acc = (acc + per_slice[i]).astype(np.float32)
+        per_slice = acc
+    return per_slice
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # scatter-add — tf.scatterAdd / InterlockedAdd (CPP.cpp:141-158); indices clamp (Steps/GraphOps.cpp:1022-1025)
 # ---------------------------------------------------------------------------------------------------------------
 def scatter_add(dst, index, src):

@@ -46,6 +46,27 @@ def fluid_step(fluid, state):
     return [vx, vy, pressure, density, state[4], state[5]], (canvas, div, res)
 
 
+def fluid_parity_mouse(step, n, m):
+    """A source that moves on a circle, so advection, the pressure solve and the canvas see non-trivial fields after a few steps."""
+    a = 0.35 * step
+    return np.array([m / 2 + 0.2 * m * np.cos(a), n / 2 + 0.2 * n * np.sin(a), 0.8 * np.cos(a + 1.0), 0.8 * np.sin(a + 1.0), 1.0], np.float32)
+
+
+def fluid_parity_run(tf, n, m, steps, vorticity=0.0):
+    """The parity scenario of the headline workload (tests/golden/make_golden_fluid.py on the oracle, tests/test_zz_fluid_gpu.py on the
+    CUDA backend): `steps` steps from rest with the moving source, outputs fed back; returns [vx, vy, pressure, density, div, canvas] of the
+    last step as numpy.  Notebook default parameters (vorticity confinement scale 0: with confinement on the program normalises the curl
+    gradient, grad / (|grad| + 1e-5), which is discontinuous where the gradient vanishes and turns last-bit differences into O(1) ones)."""
+    fluid = load_fluid(tf, n, m)
+    state = fluid_inputs(n, m)
+    state[5] = np.array([1.0, vorticity, 1.0, 1.0, 0.999, 0.999], np.float32)
+    div = canvas = None
+    for s in range(steps):
+        state[4] = fluid_parity_mouse(s, n, m)
+        state, (canvas, div, _res) = fluid_step(fluid, state)
+    return [np.array(t.numpy) for t in state[:4]] + [np.array(div.numpy), np.array(canvas.numpy)]
+
+
 # ---- C5: neural cellular automata training (examples/ML/NCA/nca.py) ---------------------------------------------------
 def load_nca(tf, batch_size, grid, pool_size=1024, train_steps=25, channel_n=12):
     """Exec the NCA example as a module with its size constants overridden; returns the module namespace

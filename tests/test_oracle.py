@@ -87,6 +87,25 @@ def test_matmul_matches_reference():
     np.testing.assert_array_equal(a.T, outs[1])
 
 
+def test_weight_gradient_matches_reference():
+    """The golden gradients of autograd_batched_dense (reference backend) against the restated per-slice-products-then-sums order, and
+    against the single contraction the CUDA backend computes instead (float64): the two agree to fp32 round-off, which is what lets
+    tfcuda_matmul_tn stand in for the reference's lowering."""
+    (x, w1, b1, w2, b2, t), outs = golden("autograd_batched_dense")
+    a = x.astype(np.float32) @ w1 + b1  # forward in numpy (fp32 round-off of the forward is far below the bars used here)
+    a = np.where(a > 0, a, np.float32(0.01) * a).astype(np.float32)
+    y = (a @ w2 + b2).astype(np.float32)
+    np.testing.assert_allclose(y, outs[1], rtol=0, atol=2e-5 * np.abs(outs[1]).max())
+    dy = (2.0 * (y - t) / y.size).astype(np.float32)
+    g_w2 = tf_oracle.matmul_weight_grad(a, dy)
+    np.testing.assert_allclose(g_w2, outs[4], rtol=0, atol=2e-5 * np.abs(outs[4]).max())
+    one_contraction = a.reshape(-1, a.shape[-1]).astype(np.float64).T @ dy.reshape(-1, dy.shape[-1]).astype(np.float64)
+    np.testing.assert_allclose(one_contraction, outs[4], rtol=0, atol=2e-5 * np.abs(outs[4]).max())
+    # the user-level x2.T @ t2 of the case: the reference's 2-D matmul order, bit for bit
+    x2, t2 = x.reshape(-1, x.shape[-1]), t.reshape(-1, t.shape[-1])
+    np.testing.assert_array_equal(tf_oracle.matmul(np.ascontiguousarray(x2.T), t2), outs[6])
+
+
 def test_scatter_add_matches_reference():
     (idx, vi, vf, vu), outs = golden("atomics")
     assert np.array_equal(tf_oracle.scatter_add(np.zeros(64, np.int32), idx, vi), outs[0])

@@ -29,7 +29,7 @@ _programs = {}
 # loops run through the CUDA emitter (TFCUDA_LIBRARY=0, read at trace time).
 LOWERINGS = ["library", "generic"]
 USES_LIBRARY = {"row_reductions", "int_reductions", "prefix_sum", "sort_radix_u32", "sort_radix_f32", "sort_radix_i32", "matmul", "qr_inverse",
-                "autograd_mlp"}
+                "autograd_mlp", "autograd_batched_dense"}
 
 
 def _run_cuda(tf, name, seed, size, lowering="library"):
