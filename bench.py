@@ -95,14 +95,14 @@ def run_reference(args):
         return 0
     sys.path.insert(0, ref)
     import numpy as np
-    import TensorFrost as tf
-    tf.initialize(tf.cpu)  # the reference's default flags: -O3 -ffast-math -fopenmp
-    from tensorfrost_b200 import workloads
     n = args.size
     devnull = os.open(os.devnull, os.O_WRONLY)
     saved = os.dup(1)
-    os.dup2(devnull, 1)  # the reference prints compile chatter on stdout; keep the JSON line clean
+    os.dup2(devnull, 1)  # the reference prints import / compile chatter on stdout; keep stdout for the ONE JSON line
     try:
+        import TensorFrost as tf
+        tf.initialize(tf.cpu)  # the reference's default flags: -O3 -ffast-math -fopenmp
+        from tensorfrost_b200 import workloads
         fluid = workloads.load_fluid(tf, n, n)
         state = [tf.tensor(a) for a in workloads.fluid_inputs(n, n)]
         for _ in range(args.warmup):
