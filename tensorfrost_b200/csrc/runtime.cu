@@ -84,6 +84,7 @@ static size_t guard_bytes() {
 
 static void* g_scratch = nullptr;
 static size_t g_scratch_bytes = 0;
+static void flush_block_cache();
 
 void* scratch(size_t bytes) {
 	if (bytes <= g_scratch_bytes) return g_scratch;
@@ -94,6 +95,12 @@ void* scratch(size_t bytes) {
 	void* p = nullptr;
 	cudaError_t e = cudaMallocAsync(&p, want, g_state.stream);
 	if (e != cudaSuccess) {
+		// parked tensor blocks / the driver pool may hold what the scratch needs: release them and ask for the exact size
+		(void)cudaGetLastError();
+		flush_block_cache();
+		cudaStreamSynchronize(g_state.stream);
+		cudaMemPool_t mp;
+		if (cudaDeviceGetDefaultMemPool(&mp, g_state.device) == cudaSuccess) cudaMemPoolTrimTo(mp, 0);
 		(void)cudaGetLastError();
 		want = bytes;
 		e = cudaMallocAsync(&p, want, g_state.stream);
@@ -145,6 +152,9 @@ static Buffer* create_buffer(size_t words) {
 		hit->second.pop_back();
 		g_blocks.bytes -= total;
 		g_blocks.hits++;
+		// the previous tenant may have been up to 63 words longer (same 256-byte class): re-zero the slack behind this tensor
+		if (payload != words * sizeof(uint32_t))
+			cudaMemsetAsync(static_cast<char*>(p) + guard + words * sizeof(uint32_t), 0, payload - words * sizeof(uint32_t), g_state.stream);
 	} else {
 		cudaError_t e = cudaMallocAsync(&p, total, g_state.stream);
 		g_blocks.driver_calls++;
