@@ -397,6 +397,7 @@ def main():
     ap.add_argument("--quick", action="store_true", help="smaller extra workloads (development)")
     ap.add_argument("--workload", default="fluid", choices=["fluid", "nca"])
     ap.add_argument("--nca-batch", type=int, default=256, help="GLOBAL batch (split across ranks: strong scaling)")
+    ap.add_argument("--nca-weak", action="store_true", help="weak scaling: --nca-batch / --nca-pool are PER GPU (e.g. --nca-batch 32 --nca-pool 128)")
     ap.add_argument("--nca-grid", type=int, default=128)
     ap.add_argument("--nca-pool", type=int, default=1024)
     ap.add_argument("--nca-steps", type=int, default=25, help="CA steps per training iteration")

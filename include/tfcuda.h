@@ -241,6 +241,12 @@ int tfcuda_matmul(uint64_t a, uint64_t b, uint64_t c, size_t batch, size_t m, si
  * (Implementations.cpp:133-135, 560-646, 243-303) with one split-K pass; deterministic (fixed-order partial sums). */
 int tfcuda_matmul_tn(uint64_t a, uint64_t b, uint64_t c, size_t r, size_t m, size_t n);
 
+/* EXPERIMENTAL (not yet run on hardware; off unless TFCUDA_MATMUL_ROWS=1): C (RxN) = A (RxK) @ B (KxN) for a small weight matrix
+ * B (N <= 128, staged in shared memory once per persistent CTA) applied to very many rows; fp32 FFMA in the reference's k order
+ * (Implementations.cpp:560-646), no TF32, no pre-pass over A.  tfcuda_matmul_rows_supported tells whether a shape qualifies. */
+int tfcuda_matmul_rows_supported(size_t r, size_t k, size_t n);
+int tfcuda_matmul_rows(uint64_t a, uint64_t b, uint64_t c, size_t r, size_t k, size_t n);
+
 /* One all-pairs gravity step on N bodies, X,V: [N,3] fp32 (n-body-benchmark.py:16-34). */
 int tfcuda_nbody_step(uint64_t x, uint64_t v, uint64_t x_new, uint64_t v_new, size_t n, float dt, float eps);
 

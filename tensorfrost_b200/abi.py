@@ -88,6 +88,8 @@ EXPORTS = {
     "tfcuda_scatter_add": (i32, [u64, u64, u64, sz, sz, i32]),
     "tfcuda_matmul": (i32, [u64, u64, u64, sz, sz, sz, sz, i32]),
     "tfcuda_matmul_tn": (i32, [u64, u64, u64, sz, sz, sz]),
+    "tfcuda_matmul_rows_supported": (i32, [sz, sz, sz]),
+    "tfcuda_matmul_rows": (i32, [u64, u64, u64, sz, sz, sz]),
     "tfcuda_nbody_step": (i32, [u64, u64, u64, u64, sz, f32, f32]),
     "tfcuda_comm_unique_id": (i32, [C.c_void_p]),
     "tfcuda_comm_init": (i32, [C.c_void_p, i32, i32]),

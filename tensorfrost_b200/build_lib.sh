@@ -26,7 +26,7 @@ if old != text:
 PY
 objs=()
 pids=()
-for f in runtime comm reduce scan radix_sort scatter nbody matmul matmul_tn matmul_tcgen05; do
+for f in runtime comm reduce scan radix_sort scatter nbody matmul matmul_tn matmul_rows matmul_tcgen05; do
   o=$OBJ/$f.o
   objs+=("$o")
   if [ ! -f "$o" ] || [ "$SRC/$f.cu" -nt "$o" ] || [ "$SRC/tfcuda_internal.h" -nt "$o" ] || [ "$HERE/../include/tfcuda.h" -nt "$o" ] \

@@ -287,6 +287,11 @@ def bench_main(args):
         torch.cuda.set_device(local)
         dist.init_process_group("gloo")  # control plane only: barrier, id broadcast, max-over-ranks
     import tensorfrost_b200
+    weak = bool(getattr(args, "nca_weak", False))
+    if weak:
+        # weak scaling: the per-GPU batch and pool shard stay at --nca-batch / --nca-pool, the global ones grow with N
+        args.nca_batch *= world
+        args.nca_pool *= world
     devnull = os.open(os.devnull, os.O_WRONLY)
     saved = os.dup(1)
     os.dup2(devnull, 1)
@@ -372,7 +377,7 @@ def bench_main(args):
         samples = args.nca_batch * args.steps
         line = {
             "metric": "NCA training samples/s", "value": samples / (ms / 1e3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"NCA training (examples/ML/NCA), global batch {args.nca_batch} of {args.nca_grid}x{args.nca_grid}x12, "
                                    f"{args.nca_steps} CA steps, pool {args.nca_pool}", "parallelism": f"dp{world}",

@@ -356,6 +356,12 @@ void DispatchCudaLibraryCall(const CudaLibraryCall& call, const TFDispatchInfo& 
 			m = a.shape[a.dim - 2];
 		}
 		if (batch * m * n == 0) return;
+		// experimental (round 1: compiled, not yet validated on hardware): small weight matrix applied to very many rows
+		static const bool rows_kernel = EnvInt("TFCUDA_MATMUL_ROWS", 0) != 0;
+		if (rows_kernel && batch == 1 && m >= 4096 && tfcuda_matmul_rows_supported(m, k, n)) {
+			Check(tfcuda_matmul_rows(Ptr(a), Ptr(b), Ptr(c), m, k, n), "matmul_rows");
+			return;
+		}
 		Check(tfcuda_matmul(Ptr(a), Ptr(b), Ptr(c), batch, m, n, k, call.params[0]), "matmul");
 	} else if (call.op == "matmul_tn") {
 		need(2, 1, 0);

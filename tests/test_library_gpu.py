@@ -238,6 +238,20 @@ def test_matmul_tn(tfcuda_lib, r, m, n):
     assert rel_err(got, tf_oracle.matmul(np.ascontiguousarray(a.T), b)) <= 1e-5 if r <= 10000 else True
 
 
+@pytest.mark.skipif(not os.environ.get("TFCUDA_EXPERIMENTAL"), reason="experimental kernel: written after round 1's GPU budget ended; enable with TFCUDA_EXPERIMENTAL=1")
+@pytest.mark.parametrize("r,k,n", [(1, 1, 1), (70, 48, 128), (5000, 48, 128), (5000, 128, 12), (5000, 12, 128), (5000, 128, 48), (257, 7, 5), (4097, 36, 30), (100000, 128, 128)])
+def test_matmul_rows(tfcuda_lib, r, k, n):
+    """Skinny matmul with the weight matrix resident in shared memory: fp32 FFMA in the reference's k order -> 1e-6 of the result scale
+    against the restatement (FMA keeps the product unrounded), like test_matmul_ffma."""
+    assert tfcuda_lib.tfcuda_matmul_rows_supported(r, k, n)
+    rng = np.random.default_rng(r + k + n)
+    a, b = rng.random((r, k), dtype=np.float32), rng.random((k, n), dtype=np.float32)
+    d_a, d_b, d_c = abi.DeviceArray(a), abi.DeviceArray(b), abi.DeviceArray(np.full((r, n), np.nan, np.float32))
+    abi.check(tfcuda_lib.tfcuda_matmul_rows(d_a.ptr, d_b.ptr, d_c.ptr, r, k, n), "matmul_rows")
+    want = tf_oracle.matmul(a, b) if r <= 5000 else (a.astype(np.float64) @ b.astype(np.float64))
+    assert rel_err(d_c.get(), want) <= (1e-6 if r <= 5000 else 2e-6)
+
+
 # ---- n-body --------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n", [1, 2, 255, 256, 257, 1500, 4096, 5000])
 def test_nbody_step(tfcuda_lib, n):
