@@ -25,6 +25,13 @@ typedef unsigned int uint;
 #define TF_RO const uint* __restrict__
 #endif
 
+// ---- programmatic dependent launch (EXPERIMENTAL, TFCUDA_PDL=1 at trace time AND at run time; not yet run on hardware) ----------
+// First statement of every emitted kernel when enabled: let the next kernel of the stream start launching its CTAs as soon as all of
+// ours are resident, then wait until every kernel before us has completed and flushed its memory.  Nothing is read or written before
+// the wait, so the program order of the stream is preserved; what overlaps is the launch latency of short dependent kernels
+// (the 32 multigrid sweeps of the fluid step: 3.6 us each for 3 MB of L2-resident data).
+TF_DEV void tf_pdl_prologue() { asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory"); }
+
 // ---- bit casts (CPP.cpp:53-96) ------------------------------------------------------------
 TF_DEV float asfloat(uint x) { return __uint_as_float(x); }
 TF_DEV float asfloat(int x) { return __int_as_float(x); }

@@ -517,6 +517,14 @@ int tfcuda_init(int device) {
 	    !load_entry("cuGetErrorString", d.GetErrorString) || !load_entry("cuFuncGetAttribute", d.FuncGetAttribute)) {
 		return 1;
 	}
+	if (getenv("TFCUDA_PDL") != nullptr && atoi(getenv("TFCUDA_PDL")) != 0) {
+		// optional entry point of the experimental programmatic-dependent-launch path; without it launches stay ordinary
+		void* p = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint("cuLaunchKernelEx", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && p)
+			d.LaunchKernelEx = reinterpret_cast<decltype(d.LaunchKernelEx)>(p);
+		(void)cudaGetLastError();
+	}
 	TFCUDA_CHECK(cudaStreamCreateWithFlags(&g_state.stream, cudaStreamNonBlocking));
 	TFCUDA_CHECK(cudaMallocHost(&g_state.pinned_word, 64));
 	TFCUDA_CHECK(cudaEventCreate(&g_state.ev_begin));
@@ -784,11 +792,31 @@ int tfcuda_launch(size_t kernel_id, const uint64_t* mem, size_t n_mem, const uin
 	const size_t kMaxGrid = 0x7fffffffull;
 	size_t done = 0;
 	ProfileScope prof(e.entry.c_str());
+	static const bool pdl_env = getenv("TFCUDA_PDL") != nullptr && atoi(getenv("TFCUDA_PDL")) != 0;
+	const bool pdl = pdl_env && g_state.drv.LaunchKernelEx != nullptr;
 	while (done < work_group_count) {
 		size_t now = std::min(kMaxGrid, work_group_count - done);
 		if (offset_word) *offset_word = vars[n_var - 1] + (uint32_t)done;
-		CUresult r = g_state.drv.LaunchKernel(e.fn, (unsigned)now, 1, 1, e.group[0], e.group[1], e.group[2], 0,
-		                                      (CUstream)g_state.stream, params, nullptr);
+		CUresult r;
+		if (pdl) {
+			// experimental: the kernel begins with griddepcontrol.wait (emitted under the same switch), so it may be scheduled while its
+			// predecessor drains; without the switch this branch is never taken
+			CUlaunchAttribute attr;
+			memset(&attr, 0, sizeof(attr));
+			attr.id = CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION;
+			attr.value.programmaticStreamSerializationAllowed = 1;
+			CUlaunchConfig cfg;
+			memset(&cfg, 0, sizeof(cfg));
+			cfg.gridDimX = (unsigned)now; cfg.gridDimY = 1; cfg.gridDimZ = 1;
+			cfg.blockDimX = e.group[0]; cfg.blockDimY = e.group[1]; cfg.blockDimZ = e.group[2];
+			cfg.sharedMemBytes = 0;
+			cfg.hStream = (CUstream)g_state.stream;
+			cfg.attrs = &attr;
+			cfg.numAttrs = 1;
+			r = g_state.drv.LaunchKernelEx(&cfg, e.fn, params, nullptr);
+		} else {
+			r = g_state.drv.LaunchKernel(e.fn, (unsigned)now, 1, 1, e.group[0], e.group[1], e.group[2], 0, (CUstream)g_state.stream, params, nullptr);
+		}
 		if (r != CUDA_SUCCESS) {
 			set_error("cuLaunchKernel(" + e.entry + ", grid=" + std::to_string(now) + ", block=" + std::to_string(e.group[0]) + "x" +
 			          std::to_string(e.group[1]) + "x" + std::to_string(e.group[2]) + "): " + drv_err(r));

@@ -22,6 +22,7 @@ struct DriverApi {
 	CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
 	CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
 	                         unsigned, CUstream, void**, void**) = nullptr;
+	CUresult (*LaunchKernelEx)(const CUlaunchConfig*, CUfunction, void**, void**) = nullptr;  // optional (TFCUDA_PDL)
 	CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
 	CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
 };

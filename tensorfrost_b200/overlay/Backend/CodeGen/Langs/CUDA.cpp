@@ -165,6 +165,9 @@ void GenerateCUDAKernel(Program* program, Kernel* kernel) {
 		main_code += "  " + kernel->var_types[i] + " var_" + kernel->var_names[i] + " = as" + kernel->var_types[i] +
 		             "(tf_a.var[" + to_string(i) + "]);\n";
 	}
+	if (const char* pdl = getenv("TFCUDA_PDL")) {
+		if (atoi(pdl) != 0) main_code += "  tf_pdl_prologue();\n";  // experimental: programmatic dependent launch (prelude.cuh)
+	}
 	main_code += "  int block_id = (int)(blockIdx.x + var__kernel_block_offset);\n";
 	main_code += "  int block_thread_id0 = (int)threadIdx.x;\n";
 	main_code += "  int block_thread_id1 = (int)threadIdx.y;\n";
