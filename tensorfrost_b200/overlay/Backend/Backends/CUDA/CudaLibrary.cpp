@@ -169,6 +169,15 @@ const Tensor* TransposedSource(const Tensor* t) {
 	Node* i1 = node->args.Get(ArgType::Index, 1);
 	if (i0->name != "dim_id" || i1->name != "dim_id") return nullptr;
 	if ((int)i0->data[0] != 1 || (int)i1->data[0] != 0) return nullptr;
+	// the load must cover the WHOLE source (a cropped or broadcast transpose is not S^T): extents equal as constants or as the same node
+	Tensors ts = t->GetShape(), ss = source->GetShape();
+	for (int d = 0; d < 2; d++) {
+		const Tensor* x = ts[d];
+		const Tensor* y = ss[1 - d];
+		int cx = x->TryGetConstant(), cy = y->TryGetConstant();
+		bool same = (x == y) || (x->node_ == y->node_) || (cx >= 0 && cx == cy);
+		if (!same) return nullptr;
+	}
 	return source;
 }
 
