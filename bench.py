@@ -301,70 +301,105 @@ def time_call(tf, fn, iters, warm=3):
 
 
 def bench_extra(tf, peaks, quick):
-    """BASELINE.json's other metrics at the configs' sizes, each against its own roofline."""
+    """BASELINE.json's other metrics at the configs' sizes, each against its own roofline.  Every section is independent: a failure is
+    recorded under its name and does not take the headline line down with it."""
     import numpy as np
     from tensorfrost_b200 import workloads
     out = {}
     rng = np.random.default_rng(0)
     hbm = peaks["hbm_gbs"]
-    # ---- radix sort, 2^28 uint32 keys (keys-only: 36 B/key algorithmic; key+value: 68 B/pair) ----
-    n = 1 << (24 if quick else 28)
-    keys = tf.cuda_tensor(rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32))
-    ms = time_call(tf, lambda: tf.cuda_radix_sort(keys), 5)
-    out["radix_sort_keys"] = {"n": n, "ms": ms, "gkeys_per_s": n / ms / 1e6, "roofline": {"bound": "hbm", "achieved": 36.0 * n / ms / 1e6, "peak": hbm,
-                              "unit": "GB/s", "frac": 36.0 * n / ms / 1e6 / hbm}}
-    vals = tf.cuda_tensor(np.arange(n, dtype=np.uint32))
-    ms = time_call(tf, lambda: tf.cuda_radix_sort(keys, vals), 5)
-    out["radix_sort_pairs"] = {"n": n, "ms": ms, "gkeys_per_s": n / ms / 1e6, "roofline": {"bound": "hbm", "achieved": 68.0 * n / ms / 1e6, "peak": hbm,
-                               "unit": "GB/s", "frac": 68.0 * n / ms / 1e6 / hbm}}
-    sort_prog = workloads.compile_sort(tf, with_values=True)  # tf.sort.radix inside a compiled program
-    ms = time_call(tf, lambda: sort_prog(keys, vals), 5)
-    out["radix_sort_pairs_program"] = {"n": n, "ms": ms, "gkeys_per_s": n / ms / 1e6, "note": "tf.sort.radix(keys, values) traced by tf.compile: one library call + output copies"}
-    del keys, vals
-    # ---- n-body, 262144 bodies: library kernel and the generic emitter on the reference program ----
-    nb = 32768 if quick else 262144
-    x = tf.cuda_tensor((5.0 * rng.standard_normal((nb, 3))).astype(np.float32))
-    v = tf.cuda_tensor(np.zeros((nb, 3), np.float32))
-    ms = time_call(tf, lambda: tf.cuda_nbody_step(x, v), 3, warm=1)
     fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
-    out["nbody_library"] = {"bodies": nb, "ms": ms, "ginteractions_per_s": nb * nb / ms / 1e6,
-                            "roofline": {"bound": "fp32", "achieved": 20.0 * nb * nb / ms / 1e9, "peak": fp32_peak, "unit": "TFLOP/s",
-                                         "frac": 20.0 * nb * nb / ms / 1e9 / fp32_peak, "note": "20 flop/interaction (SURVEY §8d C3); CUDA-core bound, not HBM"}}
-    nbody = workloads.compile_nbody(tf)
-    ms = time_call(tf, lambda: nbody(x, v), 2, warm=1)
-    out["nbody_emitted"] = {"bodies": nb, "ms": ms, "ginteractions_per_s": nb * nb / ms / 1e6}
-    # ---- row reductions over 8192^2 fp32: one read of A ----
-    m = 4096 if quick else 8192
-    a = tf.cuda_tensor(rng.random((m, m), dtype=np.float32))
-    for op in ("sum", "max", "norm"):
-        ms = time_call(tf, lambda: tf.cuda_reduce(a, -1, op), 20)
-        out[f"reduce_{op}"] = {"shape": [m, m], "ms": ms, "roofline": {"bound": "hbm", "achieved": m * m * 4 / ms / 1e6, "peak": hbm, "unit": "GB/s",
-                               "frac": m * m * 4 / ms / 1e6 / hbm}}
-    red = workloads.compile_row_reductions(tf, m)  # the compiled program: 4 library reductions -> 4 reads of A
-    ms = time_call(tf, lambda: red(a), 10)
-    out["reduce_program_4ops"] = {"shape": [m, m], "ms": ms, "roofline": {"bound": "hbm", "achieved": 4 * m * m * 4 / ms / 1e6, "peak": hbm, "unit": "GB/s",
-                                  "frac": 4 * m * m * 4 / ms / 1e6 / hbm, "note": "tf.sum/max/mean/norm in one compiled program, each a library call reading A once"}}
-    os.environ["TFCUDA_LIBRARY"] = "0"
-    red_generic = workloads.compile_row_reductions(tf, m)
-    os.environ.pop("TFCUDA_LIBRARY")
-    ms = time_call(tf, lambda: red_generic(a), 5)
-    out["reduce_program_4ops_generic_lowering"] = {"shape": [m, m], "ms": ms, "gbs_one_read": m * m * 4 / ms / 1e6}
-    # ---- matmul 8192^2 ----
-    b = tf.cuda_tensor(rng.random((m, m), dtype=np.float32))
-    mm_prog = workloads.compile_matmul(tf)
-    ms = time_call(tf, lambda: mm_prog(a, b), 10, warm=3)
-    out["matmul_program"] = {"shape": [m, m, m], "ms": ms, "tflops": 2.0 * m ** 3 / ms / 1e9, "note": "`a @ b` in a compiled program (library call, 3xTF32 mode by default)"}
-    ms = time_call(tf, lambda: tf.cuda_matmul(a, b, 2), 3, warm=1)
     tf32_peak = peaks["bf16_tflops"] / 2
-    out["matmul_ffma"] = {"shape": [m, m, m], "ms": ms, "tflops": 2.0 * m ** 3 / ms / 1e9,
-                          "roofline": {"bound": "fp32", "achieved": 2.0 * m ** 3 / ms / 1e9, "peak": fp32_peak, "unit": "TFLOP/s", "frac": 2.0 * m ** 3 / ms / 1e9 / fp32_peak}}
-    for mode, name, mult in ((0, "matmul_tcgen05_tf32", 1.0), (1, "matmul_tcgen05_3xtf32", 3.0)):
-        ms = time_call(tf, lambda: tf.cuda_matmul(a, b, mode), 10, warm=3)
-        out[name] = {"shape": [m, m, m], "ms": ms, "tflops": 2.0 * m ** 3 / ms / 1e9,
-                     "roofline": {"bound": "tensor", "achieved": mult * 2.0 * m ** 3 / ms / 1e9, "peak": tf32_peak, "unit": "TFLOP/s",
-                                  "frac": mult * 2.0 * m ** 3 / ms / 1e9 / tf32_peak,
-                                  "note": "tensor-pipe flops (3 TF32 products per fp32 product in 3xTF32 mode) incl. the transpose/split pre-pass; "
-                                          "tf32 dense peak taken as half of the measured bf16 peak"}}
+
+    def section(name, fn):
+        try:
+            fn()
+        except Exception as e:  # noqa: BLE001
+            out[name + "_error"] = f"{type(e).__name__}: {e}"[:300]
+
+    def sort_section():
+        # radix sort, 2^28 uint32 keys (keys-only: 36 B/key algorithmic; key+value: 68 B/pair)
+        n = 1 << (24 if quick else 28)
+        keys = tf.cuda_tensor(rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32))
+        ms = time_call(tf, lambda: tf.cuda_radix_sort(keys), 5)
+        out["radix_sort_keys"] = {"n": n, "ms": ms, "gkeys_per_s": n / ms / 1e6, "roofline": {"bound": "hbm", "achieved": 36.0 * n / ms / 1e6, "peak": hbm,
+                                  "unit": "GB/s", "frac": 36.0 * n / ms / 1e6 / hbm}}
+        vals = tf.cuda_tensor(np.arange(n, dtype=np.uint32))
+        ms = time_call(tf, lambda: tf.cuda_radix_sort(keys, vals), 5)
+        out["radix_sort_pairs"] = {"n": n, "ms": ms, "gkeys_per_s": n / ms / 1e6, "roofline": {"bound": "hbm", "achieved": 68.0 * n / ms / 1e6, "peak": hbm,
+                                   "unit": "GB/s", "frac": 68.0 * n / ms / 1e6 / hbm}}
+        sort_prog = workloads.compile_sort(tf, with_values=True)  # tf.sort.radix inside a compiled program
+        ms = time_call(tf, lambda: sort_prog(keys, vals), 5)
+        out["radix_sort_pairs_program"] = {"n": n, "ms": ms, "gkeys_per_s": n / ms / 1e6, "note": "tf.sort.radix(keys, values) traced by tf.compile: one library call + output copies"}
+
+    def nbody_section():
+        # n-body, 262144 bodies: library kernel and the generic emitter on the reference program
+        nb = 32768 if quick else 262144
+        x = tf.cuda_tensor((5.0 * rng.standard_normal((nb, 3))).astype(np.float32))
+        v = tf.cuda_tensor(np.zeros((nb, 3), np.float32))
+        ms = time_call(tf, lambda: tf.cuda_nbody_step(x, v), 3, warm=1)
+        out["nbody_library"] = {"bodies": nb, "ms": ms, "ginteractions_per_s": nb * nb / ms / 1e6,
+                                "roofline": {"bound": "fp32", "achieved": 20.0 * nb * nb / ms / 1e9, "peak": fp32_peak, "unit": "TFLOP/s",
+                                             "frac": 20.0 * nb * nb / ms / 1e9 / fp32_peak, "note": "20 flop/interaction (SURVEY \u00a78d C3); CUDA-core bound, not HBM"}}
+        nbody = workloads.compile_nbody(tf)
+        ms = time_call(tf, lambda: nbody(x, v), 2, warm=1)
+        out["nbody_emitted"] = {"bodies": nb, "ms": ms, "ginteractions_per_s": nb * nb / ms / 1e6}
+
+    m = 4096 if quick else 8192
+    shared = {}
+
+    def reduce_section():
+        # row reductions over 8192^2 fp32: one read of A
+        a = shared["a"] = tf.cuda_tensor(rng.random((m, m), dtype=np.float32))
+        for op in ("sum", "max", "norm"):
+            ms = time_call(tf, lambda: tf.cuda_reduce(a, -1, op), 20)
+            out[f"reduce_{op}"] = {"shape": [m, m], "ms": ms, "roofline": {"bound": "hbm", "achieved": m * m * 4 / ms / 1e6, "peak": hbm, "unit": "GB/s",
+                                   "frac": m * m * 4 / ms / 1e6 / hbm}}
+        red = workloads.compile_row_reductions(tf, m)  # the compiled program: 4 library reductions -> 4 reads of A
+        ms = time_call(tf, lambda: red(a), 10)
+        out["reduce_program_4ops"] = {"shape": [m, m], "ms": ms, "roofline": {"bound": "hbm", "achieved": 4 * m * m * 4 / ms / 1e6, "peak": hbm, "unit": "GB/s",
+                                      "frac": 4 * m * m * 4 / ms / 1e6 / hbm, "note": "tf.sum/max/mean/norm in one compiled program, each a library call reading A once"}}
+        os.environ["TFCUDA_LIBRARY"] = "0"
+        try:
+            red_generic = workloads.compile_row_reductions(tf, m)
+        finally:
+            os.environ.pop("TFCUDA_LIBRARY")
+        ms = time_call(tf, lambda: red_generic(a), 5)
+        out["reduce_program_4ops_generic_lowering"] = {"shape": [m, m], "ms": ms, "gbs_one_read": m * m * 4 / ms / 1e6}
+
+    def scan_section():
+        # inclusive prefix sum along the rows of the same matrix: one read + one write
+        a = shared.get("a")
+        if a is None:
+            a = shared["a"] = tf.cuda_tensor(rng.random((m, m), dtype=np.float32))
+        ms = time_call(tf, lambda: tf.cuda_prefix_sum(a, -1), 10)
+        out["prefix_sum_rows"] = {"shape": [m, m], "ms": ms, "roofline": {"bound": "hbm", "achieved": 2 * m * m * 4 / ms / 1e6, "peak": hbm, "unit": "GB/s",
+                                  "frac": 2 * m * m * 4 / ms / 1e6 / hbm}}
+
+    def matmul_section():
+        a = shared.get("a")
+        if a is None:
+            a = shared["a"] = tf.cuda_tensor(rng.random((m, m), dtype=np.float32))
+        b = tf.cuda_tensor(rng.random((m, m), dtype=np.float32))
+        mm_prog = workloads.compile_matmul(tf)
+        ms = time_call(tf, lambda: mm_prog(a, b), 10, warm=3)
+        out["matmul_program"] = {"shape": [m, m, m], "ms": ms, "tflops": 2.0 * m ** 3 / ms / 1e9, "note": "`a @ b` in a compiled program (library call, 3xTF32 mode by default)"}
+        ms = time_call(tf, lambda: tf.cuda_matmul(a, b, 2), 3, warm=1)
+        out["matmul_ffma"] = {"shape": [m, m, m], "ms": ms, "tflops": 2.0 * m ** 3 / ms / 1e9,
+                              "roofline": {"bound": "fp32", "achieved": 2.0 * m ** 3 / ms / 1e9, "peak": fp32_peak, "unit": "TFLOP/s", "frac": 2.0 * m ** 3 / ms / 1e9 / fp32_peak}}
+        for mode, name, mult in ((0, "matmul_tcgen05_tf32", 1.0), (1, "matmul_tcgen05_3xtf32", 3.0)):
+            ms = time_call(tf, lambda: tf.cuda_matmul(a, b, mode), 10, warm=3)
+            out[name] = {"shape": [m, m, m], "ms": ms, "tflops": 2.0 * m ** 3 / ms / 1e9,
+                         "roofline": {"bound": "tensor", "achieved": mult * 2.0 * m ** 3 / ms / 1e9, "peak": tf32_peak, "unit": "TFLOP/s",
+                                      "frac": mult * 2.0 * m ** 3 / ms / 1e9 / tf32_peak,
+                                      "note": "tensor-pipe flops (3 TF32 products per fp32 product in 3xTF32 mode) incl. the transpose/split pre-pass; "
+                                              "tf32 dense peak taken as half of the measured bf16 peak"}}
+
+    section("radix_sort", sort_section)
+    section("nbody", nbody_section)
+    section("reduce", reduce_section)
+    section("prefix_sum", scan_section)
+    section("matmul", matmul_section)
     return out
 
 
