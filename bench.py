@@ -419,6 +419,19 @@ def cpu_baseline(args):
         return {"value": None, "unit": "GB/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e}"}
 
 
+def make_line(args, world, res):
+    """The ONE JSON line of the CUDA arm (without cpu_baseline / extra, which main() adds at N = 1)."""
+    return {
+        "metric": "fused-kernel HBM GB/s", "value": res["value"], "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": res["ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"fluid_simulation {args.size}x{args.size} fp32 (BASELINE configs[1]), 1 step = 43 dispatches of 15 emitted kernels",
+                   "bytes_per_step": res["step_bytes"], "l2": "per-step working set (~20 fields x 16.8 MB) exceeds the 126 MB L2; no explicit flush",
+                   "parallelism": "replicas only (single-device program)" if world > 1 else "1 GPU"},
+        "gpu_launches": int(res["launches"]), "clocks": res["clocks"], "roofline": res["roofline"], "e2e": res["e2e"],
+        "top_kernels": res["records"],
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -460,15 +473,7 @@ def main():
     finally:
         os.dup2(saved, 1)
     if rank == 0:
-        line = {
-            "metric": "fused-kernel HBM GB/s", "value": res["value"], "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": res["ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"fluid_simulation {args.size}x{args.size} fp32 (BASELINE configs[1]), 1 step = 43 dispatches of 15 emitted kernels",
-                       "bytes_per_step": res["step_bytes"], "l2": "per-step working set (~20 fields x 16.8 MB) exceeds the 126 MB L2; no explicit flush",
-                       "parallelism": "replicas only (single-device program)" if world > 1 else "1 GPU"},
-            "gpu_launches": int(res["launches"]), "clocks": res["clocks"], "roofline": res["roofline"], "e2e": res["e2e"],
-            "top_kernels": res["records"],
-        }
+        line = make_line(args, world, res)
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args)
         if extra is not None:
