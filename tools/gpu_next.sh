@@ -23,3 +23,6 @@ TFCUDA_PDL=1 timeout 600 python bench.py --no-extra --no-cpu > "$OUT/bench_pdl.j
 TFCUDA_MATMUL_ROWS=1 timeout 600 python -m pytest tests/test_nca_gpu.py -m gpu -q > "$OUT/pytest_rows_nca.log" 2>&1; echo "rows nca parity rc=$?"; tail -3 "$OUT/pytest_rows_nca.log"
 timeout 400 python bench.py --workload nca --steps 5 --warmup 3 > "$OUT/nca_1.json" 2>/dev/null; cut -c1-300 "$OUT/nca_1.json"
 TFCUDA_MATMUL_ROWS=1 timeout 400 python bench.py --workload nca --steps 5 --warmup 3 > "$OUT/nca_1_rows.json" 2>/dev/null; cut -c1-300 "$OUT/nca_1_rows.json"
+# ncu evidence for the library kernels (round 1 has it only for the emitted fluid kernels)
+timeout 1200 ncu --set full --clock-control none --import-source on -k 'regex:onesweep|digit_histogram|gemm_tf32|reduce_rows|reduce_mid|scan|nbody|matmul_tn|split_tf32|transpose' \
+    -c 40 -f -o "$OUT/lib_full" python tools/lib_kernels_once.py > "$OUT/ncu_lib.log" 2>&1; echo "ncu lib rc=$?"
