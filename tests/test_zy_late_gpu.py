@@ -1,0 +1,54 @@
+"""GPU tests added after round 1's last GPU run (the round's GPU budget ended first).  They are collected late on purpose: the driver
+runs `pytest -x`, and every hardware-validated test should be reached before the ones whose bars were calibrated on the CPU only."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import cases
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import tf_oracle  # noqa: E402
+
+from tensorfrost_b200 import abi  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(got, want):
+    scale = max(float(np.max(np.abs(want))), 1e-30)
+    return float(np.max(np.abs(got.astype(np.float64) - want.astype(np.float64)))) / scale
+
+
+@pytest.mark.parametrize("n", [4096, 5000])
+def test_nbody_step_packed_kernel(tfcuda_lib, n):
+    """n >= 2048 takes the packed f32x2 kernel (5000 also exercises its padded tail tile).  It adds even and odd j separately: a numpy
+    emulation of that order (with 2-ulp rsqrt noise) differs from the oracle's serial sum by 1.6e-6 at n = 4096; the bar is the same 1e-5
+    as for the scalar kernel.  On hardware the two kernels agreed to 7 digits of sum|v| at 262144 bodies (profiles/r01c_nbody_variants.txt)."""
+    rng = np.random.default_rng(n)
+    x = (5.0 * rng.standard_normal((n, 3))).astype(np.float32)
+    v = (0.1 * rng.standard_normal((n, 3))).astype(np.float32)
+    d = [abi.DeviceArray(t) for t in (x, v, np.zeros_like(x), np.zeros_like(v))]
+    abi.check(tfcuda_lib.tfcuda_nbody_step(d[0].ptr, d[1].ptr, d[2].ptr, d[3].ptr, n, 0.001, 1e-4), "nbody")
+    xn, vn = tf_oracle.nbody_step(x, v)
+    assert rel_err(d[3].get(), vn) <= 1e-5 and rel_err(d[2].get(), xn) <= 1e-6
+
+
+def test_batched_dense_gradients_library_lowering(tf_cuda):
+    """autograd_batched_dense with the library lowerings on: forward products on the tcgen05 path, weight gradients and the user's
+    x2.T @ t2 through tfcuda_matmul_tn.  (The generic lowering of the same case runs in tests/test_parity_gpu.py and was green on hardware;
+    the NCA golden test covers tfcuda_matmul_tn inside a real training step.)"""
+    name = "autograd_batched_dense"
+    g = np.load(os.path.join(HERE, "golden", f"{name}.npz"))
+    want = []
+    while f"out{len(want)}" in g:
+        want.append(g[f"out{len(want)}"])
+    os.environ["TFCUDA_LIBRARY"] = "1"
+    try:
+        got, _ = cases.run_case(tf_cuda, name, seed=int(g["seed"]), size=int(g["size"]))
+    finally:
+        os.environ.pop("TFCUDA_LIBRARY", None)
+    cases.compare(cases.CASES[name], got, want)
