@@ -1,0 +1,231 @@
+"""TEST INFRASTRUCTURE ONLY.  Executes the CUDA C++ the emitter produces — the exact text NVRTC compiles for sm_100a — on the HOST:
+every case of tests/cases.py is traced by the CUDA-enabled module in codegen mode (generic lowering: library calls have no text), its
+emitted kernels are compiled by g++ through tests/cpu_sim/cuda_host_shim.h, the host program the reference generated is compiled next to
+tests/cpu_sim/sim_runtime.inc, and the program is run on the case's seeded inputs.  The outputs go to an .npz for the caller to compare
+with the reference's golden fixtures.  What this checks without a GPU: the kernel wrapper and argument block, binding / variable order,
+block and thread index arithmetic, the prelude's helper semantics, atomics, host-side loops and read/write callbacks.  What it cannot
+check: anything that depends on the hardware (CUDA math library rounding, real parallel execution, barriers).
+
+usage: python tests/cpu_sim/run_sim.py <out.npz> <case[:size[:seed]]|fluid> [...]      (own process: the backend is a process singleton)
+"""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+TESTS = os.path.dirname(HERE)
+ROOT = os.path.dirname(TESTS)
+sys.path.insert(0, TESTS)
+sys.path.insert(0, ROOT)
+
+
+class SimTensor(C.Structure):
+    _fields_ = [("data", C.POINTER(C.c_uint32)), ("dim", C.c_size_t), ("shape", C.c_size_t * 8), ("type", C.c_int)]
+
+
+TYPE_OF = {"f": 0, "u": 1, "i": 2, "b": 3}
+
+
+def to_words(a):
+    a = np.asarray(a)
+    if a.dtype == np.bool_:
+        return np.ascontiguousarray(a.astype(np.uint32)), 3
+    if a.dtype.kind == "f":
+        return np.ascontiguousarray(a.astype(np.float32)).view(np.uint32), 0
+    if a.dtype.kind == "u":
+        return np.ascontiguousarray(a.astype(np.uint32)), 1
+    if a.dtype.kind == "i":
+        return np.ascontiguousarray(a.astype(np.int32)).view(np.uint32), 2
+    raise TypeError(f"unsupported input dtype {a.dtype}")
+
+
+def from_words(words, shape, type_id):
+    words = words.reshape(shape)
+    if type_id == 0:
+        return words.view(np.float32)
+    if type_id == 2:
+        return words.view(np.int32)
+    if type_id == 3:
+        return words != 0
+    return words
+
+
+def kernel_units(kernels, host_code):
+    """C++ text of the kernels translation unit: shim + prelude + emitted kernels + one serial launcher per kernel."""
+    groups = {}
+    for line in host_code.splitlines():
+        m = re.search(r"tf\.dispatch\((\d+),.*\{([^{}]*)\}\);\s*$", line)
+        if m:
+            g = [int(x) for x in m.group(2).replace(" ", "").split(",") if x]
+            groups[int(m.group(1))] = (g + [1, 1, 1])[:3]
+    text = ['#include "cuda_host_shim.h"', open(os.path.join(ROOT, "tensorfrost_b200", "csrc", "prelude.cuh")).read()]
+    cases_ = []
+    for k in kernels:
+        src = k[0][1] + k[0][2]
+        if "tfcuda_lib:" in src:
+            raise RuntimeError("library-call kernels have no text to execute: trace with TFCUDA_LIBRARY=0")
+        if "tf_group_barrier" in src:
+            raise RuntimeError("kernels that need a block barrier cannot run serially on the host")
+        m = re.search(r"void (?:__launch_bounds__\(\d+\) )?kernel_(\d+)\(", src)
+        kid = int(m.group(1))
+        nm = re.search(r"uint\* mem\[(\d+)\];", src)
+        nv = re.search(r"uint var\[(\d+)\];", src)
+        n_mem, n_var = (int(nm.group(1)) if nm else 0), int(nv.group(1))
+        gx, gy, gz = groups.get(kid, (None, None, None))
+        if gx is None:
+            continue  # never dispatched by this program
+        text.append(src)
+        fill_mem = f"for (size_t i = 0; i < {n_mem}; i++) a.mem[i] = mem[i];" if n_mem else ""
+        text.append(f"""
+static int launch_{kid}(uint32_t** mem, size_t n_mem, const uint32_t* vars, size_t n_var, size_t wgc) {{
+  if (n_mem != {n_mem} || n_var != {n_var}) return 2;
+  kernel_{kid}_args a;
+  {fill_mem}
+  for (size_t i = 0; i < {n_var}; i++) a.var[i] = vars[i];
+  gridDim = sim_dim3{{(unsigned)wgc, 1, 1}};
+  blockDim = sim_dim3{{{gx}, {gy}, {gz}}};
+  for (size_t b = 0; b < wgc; b++) {{
+    blockIdx = sim_dim3{{(unsigned)b, 0, 0}};
+    for (unsigned z = 0; z < {gz}; z++) for (unsigned y = 0; y < {gy}; y++) for (unsigned x = 0; x < {gx}; x++) {{
+      threadIdx = sim_dim3{{x, y, z}};
+      kernel_{kid}(a);
+    }}
+  }}
+  return 0;
+}}""")
+        cases_.append(f"    case {kid}: return launch_{kid}(mem, n_mem, vars, n_var, wgc);")
+    text.append('extern "C" int sim_kernel_launch(size_t kernel_id, uint32_t** mem, size_t n_mem, const uint32_t* vars, size_t n_var, size_t wgc) {\n'
+                "  switch (kernel_id) {\n" + "\n".join(cases_) + "\n    default: return 1;\n  }\n}\n")
+    return "\n".join(text)
+
+
+def build(host_code, kernels, tag):
+    """g++ the two translation units (emitted kernels through the shim; generated host program + sim runtime) into one library."""
+    work = tempfile.mkdtemp(prefix=f"tfsim_{tag}_")
+    with open(os.path.join(work, "kernels.cpp"), "w") as f:
+        f.write(kernel_units(kernels, host_code))
+    with open(os.path.join(work, "host.cpp"), "w") as f:
+        f.write("#define main tf_program_main\n" + host_code + "\n" + open(os.path.join(HERE, "sim_runtime.inc")).read())
+    so = os.path.join(work, "sim.so")
+    cmd = ["g++", "-O2", "-std=c++17", "-w", "-shared", "-fPIC", "-include", "math.h", "-I", HERE, os.path.join(work, "kernels.cpp"),
+           os.path.join(work, "host.cpp"), "-o", so]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"g++ failed for {tag}:\n{r.stderr[-3000:]}")
+    lib = C.CDLL(so)
+    lib.sim_run.argtypes = [C.POINTER(SimTensor), C.c_int, C.POINTER(SimTensor), C.c_int]
+    lib.sim_run.restype = C.c_int
+    lib.sim_error.restype = C.c_char_p
+    lib.sim_free.argtypes = [C.c_void_p]
+    return lib
+
+
+def run(lib, inputs, n_out, tag):
+    ins = (SimTensor * max(len(inputs), 1))()
+    keep = []
+    for i, a in enumerate(inputs):
+        words, type_id = to_words(a)
+        keep.append(words)
+        ins[i].data = words.ctypes.data_as(C.POINTER(C.c_uint32))
+        ins[i].dim = words.ndim
+        for d, s in enumerate(words.shape):
+            ins[i].shape[d] = s
+        ins[i].type = type_id
+    outs = (SimTensor * max(n_out, 1))()
+    if lib.sim_run(ins, len(inputs), outs, n_out) != 0:
+        raise RuntimeError(f"sim_run failed for {tag}: {lib.sim_error().decode(errors='replace')}")
+    result = []
+    for i in range(n_out):
+        shape = tuple(outs[i].shape[d] for d in range(outs[i].dim))
+        n = int(np.prod(shape)) if shape else 1
+        words = np.ctypeslib.as_array(outs[i].data, shape=(n,)).copy()
+        lib.sim_free(outs[i].data)
+        result.append(from_words(words, shape, outs[i].type))
+    return result
+
+
+class HostTensor:
+    """What a program call returns in the fluid scenario: the `.numpy` the workload helpers read."""
+
+    def __init__(self, array):
+        self.numpy = array
+
+
+def main():
+    out_path, specs = sys.argv[1], sys.argv[2:]
+    os.environ["TFCUDA_LIBRARY"] = "0"
+    import tensorfrost_b200
+    from tensorfrost_b200 import workloads
+    tf = tensorfrost_b200.import_module()
+    saved = os.dup(1)
+    os.dup2(os.open(os.devnull, os.O_WRONLY), 1)
+    result = {}
+    try:
+        tf.initialize(tf.codegen, "", tf.cuda_lang)
+        import cases
+        captured = []
+        keep = []  # programs must stay alive: the module's kernel registry holds raw pointers into them (Backend/KernelManager.cpp:4-8)
+        real_compile = tf.compile
+
+        def capturing_compile(fn):
+            p = real_compile(fn)
+            captured.append(p)
+            keep.append(p)
+            return p
+        tf.compile = capturing_compile
+        seen = 0
+        for spec in specs:
+            parts = spec.split(":")
+            name = parts[0]
+            del captured[:]
+            if name == "fluid":
+                n, m, steps = (int(v) for v in parts[1:4])
+                fluid = workloads.load_fluid(tf, n, m)
+                kernels = tf.get_all_generated_kernels()[seen:]
+                seen += len(kernels)
+                lib = build(fluid.compiled_code(), kernels, "fluid")
+
+                def call(*state):
+                    arrays = [t.numpy if isinstance(t, HostTensor) else t for t in state]
+                    return [HostTensor(o) for o in run(lib, arrays, 7, "fluid")]
+                state = workloads.fluid_inputs(n, m)
+                state[5] = np.array([1.0, 0.0, 1.0, 1.0, 0.999, 0.999], np.float32)  # as tensorfrost_b200.workloads.fluid_parity_run
+                div = canvas = None
+                for step in range(steps):
+                    state[4] = workloads.fluid_parity_mouse(step, n, m)
+                    state, (canvas, div, _res) = workloads.fluid_step(call, state)
+                outs = [t.numpy if isinstance(t, HostTensor) else t for t in state[:4]] + [div.numpy, canvas.numpy]
+                for k, o in enumerate(outs):
+                    result[f"{spec}/{k}"] = o
+                continue
+            size = int(parts[1]) if len(parts) > 1 and parts[1] else None
+            seed = int(parts[2]) if len(parts) > 2 else 0
+            c = cases.CASES[name]
+            inputs = c.make_inputs(np.random.default_rng(seed), size or c.default_size)
+            prog = c.build(tf)
+            if not captured:  # compiled on first call with the actual extents: codegen mode compiles, then refuses to execute
+                try:
+                    prog(*inputs)
+                except RuntimeError:
+                    pass
+            program = captured[-1]
+            kernels = tf.get_all_generated_kernels()[seen:]
+            seen += len(kernels)
+            n_out = len(re.findall(r"\bout\[\d+\]\s*=", program.compiled_code()))
+            print(f"[run_sim] {name}: {len(kernels)} kernels, {n_out} outputs", file=sys.stderr, flush=True)
+            outs = run(build(program.compiled_code(), kernels, name), inputs, n_out, name)
+            for k, o in enumerate(outs):
+                result[f"{spec}/{k}"] = o
+    finally:
+        os.dup2(saved, 1)
+    np.savez(out_path, **result)
+    print(f"[run_sim] {len(specs)} programs executed on the host from their emitted CUDA text")
+
+
+if __name__ == "__main__":
+    main()
