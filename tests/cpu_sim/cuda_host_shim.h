@@ -3,13 +3,16 @@
 // prelude helpers, atomics) can be checked against the reference's golden outputs without a GPU.  Nothing under tensorfrost_b200/
 // includes this file; it is not a backend and not a fallback.
 //
-// Model: blocks and the threads of a block run serially to completion (so atomics are plain read-modify-writes and __shared__ arrays
-// are statics shared by the serial threads of the current block).  Kernels that need a real barrier cannot run this way: the runner
-// refuses any kernel whose text calls tf_group_barrier.
+// Model: blocks run one after the other.  The threads of a block run serially to completion, except for kernels whose text calls
+// tf_group_barrier: those get one host thread per CUDA thread of the block and a std::barrier (threads that return early drop out of
+// it, as exited CUDA threads do).  __shared__ arrays are statics shared by the threads of the current block; atomics are real atomics.
 #pragma once
+#include <barrier>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <thread>
+#include <vector>
 
 #define TF_HOST_SIM 1
 #define __global__
@@ -22,7 +25,8 @@
 #define __shared__ static
 
 struct sim_dim3 { unsigned x, y, z; };
-static sim_dim3 blockIdx, threadIdx, blockDim, gridDim;
+static thread_local sim_dim3 blockIdx, threadIdx, blockDim, gridDim;
+static std::barrier<>* sim_block_barrier = nullptr;  // set by the launcher of a kernel that uses barriers
 
 static inline float __uint_as_float(unsigned v) { float f; std::memcpy(&f, &v, 4); return f; }
 static inline float __int_as_float(int v) { float f; std::memcpy(&f, &v, 4); return f; }
@@ -35,16 +39,32 @@ static inline unsigned __brev(unsigned v) {
 	v = ((v >> 8) & 0x00ff00ffu) | ((v & 0x00ff00ffu) << 8);
 	return (v >> 16) | (v << 16);
 }
-static inline void __syncthreads() {}
-
-template <typename T> static inline T atomicAdd(T* p, T v) { T old = *p; *p = old + v; return old; }
-template <typename T> static inline T atomicMin(T* p, T v) { T old = *p; *p = v < old ? v : old; return old; }
-template <typename T> static inline T atomicMax(T* p, T v) { T old = *p; *p = v > old ? v : old; return old; }
-template <typename T> static inline T atomicAnd(T* p, T v) { T old = *p; *p = old & v; return old; }
-template <typename T> static inline T atomicOr(T* p, T v) { T old = *p; *p = old | v; return old; }
-template <typename T> static inline T atomicXor(T* p, T v) { T old = *p; *p = old ^ v; return old; }
-static inline unsigned atomicCAS(unsigned* p, unsigned expected, unsigned desired) {
-	unsigned old = *p;
-	if (old == expected) *p = desired;
-	return old;
+static inline void __syncthreads() {
+	if (sim_block_barrier) sim_block_barrier->arrive_and_wait();
 }
+
+static inline unsigned atomicCAS(unsigned* p, unsigned expected, unsigned desired) {
+	__atomic_compare_exchange_n(p, &expected, desired, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+	return expected;  // the value seen
+}
+template <typename T> static inline T atomicAdd(T* p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+template <> inline float atomicAdd<float>(float* p, float v) {
+	unsigned* u = reinterpret_cast<unsigned*>(p);
+	unsigned cur = __atomic_load_n(u, __ATOMIC_SEQ_CST);
+	for (;;) {
+		unsigned want = __float_as_uint(__uint_as_float(cur) + v);
+		unsigned seen = atomicCAS(u, cur, want);
+		if (seen == cur) return __uint_as_float(cur);
+		cur = seen;
+	}
+}
+template <typename T> static inline T sim_atomic_rmw(T* p, T v, T (*op)(T, T)) {
+	T cur = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+	while (!__atomic_compare_exchange_n(p, &cur, op(cur, v), false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+	return cur;
+}
+template <typename T> static inline T atomicMin(T* p, T v) { return sim_atomic_rmw<T>(p, v, [](T a, T b) { return b < a ? b : a; }); }
+template <typename T> static inline T atomicMax(T* p, T v) { return sim_atomic_rmw<T>(p, v, [](T a, T b) { return b > a ? b : a; }); }
+template <typename T> static inline T atomicAnd(T* p, T v) { return __atomic_fetch_and(p, v, __ATOMIC_SEQ_CST); }
+template <typename T> static inline T atomicOr(T* p, T v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+template <typename T> static inline T atomicXor(T* p, T v) { return __atomic_fetch_xor(p, v, __ATOMIC_SEQ_CST); }

@@ -69,8 +69,7 @@ def kernel_units(kernels, host_code):
         src = k[0][1] + k[0][2]
         if "tfcuda_lib:" in src:
             raise RuntimeError("library-call kernels have no text to execute: trace with TFCUDA_LIBRARY=0")
-        if "tf_group_barrier" in src:
-            raise RuntimeError("kernels that need a block barrier cannot run serially on the host")
+        needs_barrier = "tf_group_barrier" in src
         m = re.search(r"void (?:__launch_bounds__\(\d+\) )?kernel_(\d+)\(", src)
         kid = int(m.group(1))
         nm = re.search(r"uint\* mem\[(\d+)\];", src)
@@ -81,6 +80,30 @@ def kernel_units(kernels, host_code):
             continue  # never dispatched by this program
         text.append(src)
         fill_mem = f"for (size_t i = 0; i < {n_mem}; i++) a.mem[i] = mem[i];" if n_mem else ""
+        if needs_barrier:
+            body = f"""
+    blockIdx = sim_dim3{{(unsigned)b, 0, 0}};
+    std::barrier<> bar({gx} * {gy} * {gz});
+    sim_block_barrier = &bar;
+    std::vector<std::thread> threads;
+    for (unsigned z = 0; z < {gz}; z++) for (unsigned y = 0; y < {gy}; y++) for (unsigned x = 0; x < {gx}; x++)
+      threads.emplace_back([&a, &bar, b, x, y, z, wgc]() {{
+        gridDim = sim_dim3{{(unsigned)wgc, 1, 1}};
+        blockDim = sim_dim3{{{gx}, {gy}, {gz}}};
+        blockIdx = sim_dim3{{(unsigned)b, 0, 0}};
+        threadIdx = sim_dim3{{x, y, z}};
+        kernel_{kid}(a);
+        bar.arrive_and_drop();  // an exited CUDA thread no longer takes part in the block's barriers
+      }});
+    for (auto& t : threads) t.join();
+    sim_block_barrier = nullptr;"""
+        else:
+            body = f"""
+    blockIdx = sim_dim3{{(unsigned)b, 0, 0}};
+    for (unsigned z = 0; z < {gz}; z++) for (unsigned y = 0; y < {gy}; y++) for (unsigned x = 0; x < {gx}; x++) {{
+      threadIdx = sim_dim3{{x, y, z}};
+      kernel_{kid}(a);
+    }}"""
         text.append(f"""
 static int launch_{kid}(uint32_t** mem, size_t n_mem, const uint32_t* vars, size_t n_var, size_t wgc) {{
   if (n_mem != {n_mem} || n_var != {n_var}) return 2;
@@ -89,12 +112,7 @@ static int launch_{kid}(uint32_t** mem, size_t n_mem, const uint32_t* vars, size
   for (size_t i = 0; i < {n_var}; i++) a.var[i] = vars[i];
   gridDim = sim_dim3{{(unsigned)wgc, 1, 1}};
   blockDim = sim_dim3{{{gx}, {gy}, {gz}}};
-  for (size_t b = 0; b < wgc; b++) {{
-    blockIdx = sim_dim3{{(unsigned)b, 0, 0}};
-    for (unsigned z = 0; z < {gz}; z++) for (unsigned y = 0; y < {gy}; y++) for (unsigned x = 0; x < {gx}; x++) {{
-      threadIdx = sim_dim3{{x, y, z}};
-      kernel_{kid}(a);
-    }}
+  for (size_t b = 0; b < wgc; b++) {{{body}
   }}
   return 0;
 }}""")
@@ -112,11 +130,15 @@ def build(host_code, kernels, tag):
     with open(os.path.join(work, "host.cpp"), "w") as f:
         f.write("#define main tf_program_main\n" + host_code + "\n" + open(os.path.join(HERE, "sim_runtime.inc")).read())
     so = os.path.join(work, "sim.so")
-    cmd = ["g++", "-O2", "-std=c++17", "-w", "-shared", "-fPIC", "-include", "math.h", "-I", HERE, os.path.join(work, "kernels.cpp"),
-           os.path.join(work, "host.cpp"), "-o", so]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    # two translation units: the kernels need C++20 (<barrier>), the generated host program defines its own lerp() and must stay C++17
+    common = ["g++", "-O2", "-pthread", "-w", "-fPIC", "-include", "math.h", "-I", HERE, "-c"]
+    for std, unit in (("-std=c++20", "kernels"), ("-std=c++17", "host")):
+        r = subprocess.run(common + [std, os.path.join(work, unit + ".cpp"), "-o", os.path.join(work, unit + ".o")], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"g++ failed for {tag} ({unit}):\n{r.stderr[-3000:]}")
+    r = subprocess.run(["g++", "-shared", "-pthread", os.path.join(work, "kernels.o"), os.path.join(work, "host.o"), "-o", so], capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError(f"g++ failed for {tag}:\n{r.stderr[-3000:]}")
+        raise RuntimeError(f"link failed for {tag}:\n{r.stderr[-3000:]}")
     lib = C.CDLL(so)
     lib.sim_run.argtypes = [C.POINTER(SimTensor), C.c_int, C.POINTER(SimTensor), C.c_int]
     lib.sim_run.restype = C.c_int

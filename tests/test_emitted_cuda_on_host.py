@@ -1,6 +1,6 @@
 """CPU test: the CUDA C++ the emitter produces (the exact text NVRTC compiles for sm_100a) is compiled by g++ through a host shim and
-EXECUTED on the host, for every parity case whose kernels need no block barrier and for the 10-step fluid scenario, and the results
-are compared with the golden outputs of the reference's own C++/OpenMP backend (tests/cpu_sim/run_sim.py; test infrastructure only).
+EXECUTED on the host, for every parity case and for the 10-step fluid scenario (kernels that use tf.group_barrier get one host thread
+per CUDA thread of a block and a std::barrier), and the results are compared with the golden outputs of the reference's own C++/OpenMP backend (tests/cpu_sim/run_sim.py; test infrastructure only).
 
 This pins, without a GPU, everything about an emitted program that is not hardware: the kernel wrapper and argument block, binding
 and variable order, block / thread index arithmetic, tail guards, the prelude's helper semantics (min/max/sign/pcg/... quirks included),
@@ -18,7 +18,6 @@ import cases
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 GOLDEN = os.path.join(HERE, "golden")
-NEEDS_BARRIER = {"sort_radix_u32", "sort_radix_f32", "sort_radix_i32"}  # group-shared histograms with tf.group_barrier
 FLUID_NAMES = ["vx", "vy", "pressure", "density", "div", "canvas"]
 
 
@@ -38,7 +37,7 @@ def test_emitted_kernels_reproduce_the_reference_on_the_host(tmp_path):
         pytest.skip("CUDA-enabled module not built here (build() needs the reference sources)")
     if not os.path.exists(os.path.join(ROOT, "build", "workloads", "fluid_program.py.txt")):
         pytest.skip("benchmark programs not extracted")
-    names = [n for n in sorted(cases.CASES) if n not in NEEDS_BARRIER]
+    names = sorted(cases.CASES)
     specs = {}
     for n in names:
         size, seed, _ = _golden(n)
