@@ -225,6 +225,30 @@ def main():
                 for k, o in enumerate(outs):
                     result[f"{spec}/{k}"] = o
                 continue
+            if name == "nca":
+                # the grad program of the data-parallel NCA step at the golden configuration, inputs as NcaTrainer.__init__ makes them
+                from tensorfrost_b200 import nca_dp
+                g = np.load(os.path.join(TESTS, "golden", "nca_step.npz"))
+                batch, grid, pool_size, steps = int(g["global_batch"]), int(g["grid"]), int(g["pool_size"]), int(g["train_steps"])
+                nca = workloads.load_nca(tf, batch, grid, pool_size=pool_size, train_steps=steps, channel_n=12)
+                grad_step, _apply, _mono, shapes = nca_dp.build_programs(tf, nca, steps)
+                program = tf.compile(grad_step)
+                kernels = tf.get_all_generated_kernels()[seen:]
+                seen += len(kernels)
+                rng = np.random.default_rng(0)
+                hidden = 128
+                fc1 = (rng.standard_normal((48, hidden)) * np.sqrt(2.0 / 48)).astype(np.float32)
+                zeros = lambda *sh: np.zeros(sh, np.float32)  # noqa: E731
+                trainable = [fc1, zeros(hidden), zeros(hidden, 12), zeros(12)]
+                # input order of the traced program (its check_tensor lines): model parameters, filters, seed, Adam t, m[4], v[4], pool, image
+                inputs = trainable + [workloads.nca_filters(), np.array([0], np.uint32), zeros(1)] + [np.zeros_like(t) for t in trainable] \
+                    + [np.zeros_like(t) for t in trainable] + [workloads.nca_pool(pool_size, grid, 12), workloads.nca_target(grid, 0),
+                                                               np.asarray(g["ids"], np.int32), np.array([float(nca.CELL_FIRE_RATE)], np.float32)]
+                print(f"[run_sim] nca grad program: {len(kernels)} kernels", file=sys.stderr, flush=True)
+                outs = run(build(program.compiled_code(), kernels, "nca"), inputs, 4, "nca")
+                for k, o in enumerate(outs):
+                    result[f"{spec}/{k}"] = o
+                continue
             size = int(parts[1]) if len(parts) > 1 and parts[1] else None
             seed = int(parts[2]) if len(parts) > 2 else 0
             c = cases.CASES[name]

@@ -1,5 +1,5 @@
 """CPU test: the CUDA C++ the emitter produces (the exact text NVRTC compiles for sm_100a) is compiled by g++ through a host shim and
-EXECUTED on the host, for every parity case and for the 10-step fluid scenario (kernels that use tf.group_barrier get one host thread
+EXECUTED on the host, for every parity case, for the 10-step fluid scenario and for the NCA grad program (kernels that use tf.group_barrier get one host thread
 per CUDA thread of a block and a std::barrier), and the results are compared with the golden outputs of the reference's own C++/OpenMP backend (tests/cpu_sim/run_sim.py; test infrastructure only).
 
 This pins, without a GPU, everything about an emitted program that is not hardware: the kernel wrapper and argument block, binding
@@ -45,7 +45,7 @@ def test_emitted_kernels_reproduce_the_reference_on_the_host(tmp_path):
     fluid = np.load(os.path.join(GOLDEN, "fluid_128.npz"))
     fluid_spec = f"fluid:{int(fluid['n'])}:{int(fluid['n'])}:{int(fluid['steps'])}"
     out = str(tmp_path / "sim.npz")
-    r = subprocess.run([sys.executable, os.path.join(HERE, "cpu_sim", "run_sim.py"), out] + list(specs.values()) + [fluid_spec],
+    r = subprocess.run([sys.executable, os.path.join(HERE, "cpu_sim", "run_sim.py"), out] + list(specs.values()) + [fluid_spec, "nca"],
                        cwd=str(tmp_path), capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0, r.stderr[-3000:]
     got = np.load(out)
@@ -58,4 +58,14 @@ def test_emitted_kernels_reproduce_the_reference_on_the_host(tmp_path):
     for k, name in enumerate(FLUID_NAMES):
         a, b = got[f"{fluid_spec}/{k}"].astype(np.float64), fluid[name].astype(np.float64)
         assert np.abs(a - b).max() <= 1e-6 * np.abs(b).max(), f"fluid {name}"
-    print(f"{exact} of {len(names)} cases bit-identical to the reference")
+    # the grad program of the data-parallel NCA step (83 emitted kernels: 3 CA steps, autodiff, float atomics, and the reference's
+    # out-of-range neighbour read, which the zero guard bands make deterministic) against the reference's gradients, loss and state
+    nca = np.load(os.path.join(GOLDEN, "nca_step.npz"))
+    flat, state = got["nca/2"], got["nca/3"]
+    assert flat.shape == nca["flat0"].shape
+    scale = np.abs(nca["flat0"][:-1]).max()
+    assert np.abs(flat[:-1].astype(np.float64) - nca["flat0"][:-1]).max() <= 1e-5 * scale
+    assert abs(float(flat[-1]) - float(nca["split_losses"][0])) <= 1e-6
+    assert np.abs(state - nca["state0"]).max() <= 2.0 / 255.0 + 1e-6 and np.mean(np.abs(state - nca["state0"]) > 1e-6) < 0.02
+    print(f"{exact} of {len(names)} cases bit-identical to the reference; NCA gradients max |diff| "
+          f"{np.abs(flat[:-1].astype(np.float64) - nca['flat0'][:-1]).max():.1e}")
