@@ -8,7 +8,8 @@ Bars (relative to each field's max magnitude after the 10 steps): 2e-5 for vx / 
 difference of neighbouring velocities, its own scale is 10x smaller).  Calibration: the oracle itself moves by <= 2.2e-6 (fields),
 <= 8.5e-6 (div), <= 5.2e-6 (canvas) between strict flags, FMA contraction (-mfma -ffp-contract=fast: what nvcc does) and the reference's
 default -ffast-math (numbers printed by make_golden_fluid.py); the bars leave ~10x on top of that for the GPU's own expf / sqrtf / division
-rounding over 10 steps of a multigrid solve.  north_star's single-operation bar is 1e-5.
+rounding over 10 steps of a multigrid solve.  north_star's single-operation bar is 1e-5.  The emitted kernels themselves reproduce this fixture
+bit for bit when executed on the host (tests/test_emitted_cuda_on_host.py), so whatever this test sees is the hardware's arithmetic.
 (File name: collected last, so the rest of the GPU suite is reported before this long-running scenario.)"""
 import os
 import subprocess
