@@ -135,7 +135,16 @@ void GenerateCUDAKernel(Program* program, Kernel* kernel) {
 		RegisterCudaLibraryKernel(kernel);
 		kernel->generated_header_ = "";
 		kernel->generated_bindings_ = "";
-		kernel->generated_main_ = "// " + kname + ": " + kernel->root->debug_name + " -> hand-written kernel in libtfcuda.so\n";
+		// the comment also records which binding plays which role (tests/cpu_sim replays library-lowered programs on the host from it)
+		string roles;
+		if (const CudaLibraryCall* call = FindCudaLibraryCall(kernel->kernel_id_)) {
+			roles = " inputs=[";
+			for (size_t i = 0; i < call->inputs.size(); i++) roles += (i ? "," : "") + to_string(call->inputs[i]);
+			roles += "] outputs=[";
+			for (size_t i = 0; i < call->outputs.size(); i++) roles += (i ? "," : "") + to_string(call->outputs[i]);
+			roles += "]";
+		}
+		kernel->generated_main_ = "// " + kname + ": " + kernel->root->debug_name + roles + " -> hand-written kernel in libtfcuda.so\n";
 		kernel->full_generated_code_ = kernel->generated_main_;
 		return;
 	}

@@ -68,7 +68,7 @@ def kernel_units(kernels, host_code):
     for k in kernels:
         src = k[0][1] + k[0][2]
         if "tfcuda_lib:" in src:
-            raise RuntimeError("library-call kernels have no text to execute: trace with TFCUDA_LIBRARY=0")
+            continue  # a library call: no text; handled by the library callback (library_calls below)
         needs_barrier = "tf_group_barrier" in src
         m = re.search(r"void (?:__launch_bounds__\(\d+\) )?kernel_(\d+)\(", src)
         kid = int(m.group(1))
@@ -122,6 +122,71 @@ static int launch_{kid}(uint32_t** mem, size_t n_mem, const uint32_t* vars, size
     return "\n".join(text)
 
 
+def library_calls(kernels):
+    """kernel id -> (op, params, input bindings, output bindings) from the marker comments of library-call kernels."""
+    calls = {}
+    for k in kernels:
+        m = re.search(r"// kernel_(\d+): tfcuda_lib:([a-z_]+)((?::-?\d+)*) inputs=\[([\d,]*)\] outputs=\[([\d,]*)\]", k[0][2])
+        if m:
+            ints = lambda t: [int(x) for x in t.split(",") if x]  # noqa: E731
+            calls[int(m.group(1))] = (m.group(2), [int(x) for x in m.group(3).split(":") if x], ints(m.group(4)), ints(m.group(5)))
+    return calls
+
+
+REDUCE_OPS = {0: "sum", 1: "max", 2: "min", 3: "mean", 4: "norm"}  # TFCUDA_RED_* of include/tfcuda.h
+
+
+def make_library_callback(calls):
+    """The host stand-in for libtfcuda's library kernels: the numpy restatement of the reference algorithms (oracle/tf_oracle.py), applied
+    with the same role / extent / axis conventions as DispatchCudaLibraryCall (overlay/Backend/Backends/CUDA/CudaLibrary.cpp)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import tf_oracle
+    dtypes = {0: np.float32, 1: np.uint32, 2: np.int32, 3: np.uint32}
+
+    def view(t):
+        shape = tuple(t.shape[d] for d in range(t.dim))
+        n = int(np.prod(shape)) if shape else 1
+        return np.ctypeslib.as_array(t.data, shape=(n,)).view(dtypes[t.type]).reshape(shape)
+
+    def callback(kernel_id, n_tensors, tensors):
+        if kernel_id not in calls:
+            return 0
+        try:
+            op, params, ins, outs = calls[kernel_id]
+            t = [view(tensors[i]) for i in range(n_tensors)]
+            if op == "matmul":
+                a, b, c = t[ins[0]], t[ins[1]], t[outs[0]]
+                c[...] = tf_oracle.matmul(a, b).reshape(c.shape)
+            elif op == "matmul_tn":
+                a, b, c = t[ins[0]], t[ins[1]], t[outs[0]]
+                m, n = a.shape[-1], b.shape[-1]
+                c[...] = (a.reshape(-1, m).astype(np.float64).T @ b.reshape(-1, n).astype(np.float64)).astype(np.float32).reshape(c.shape)
+            elif op == "reduce":
+                src, dst = t[ins[0]], t[outs[0]]
+                axis = src.ndim - 1 - params[1]  # IR dims are innermost-first
+                dst[...] = np.asarray(tf_oracle.reduce(src, axis, REDUCE_OPS[params[0]])).reshape(dst.shape)
+            elif op == "scan":
+                src, dst = t[ins[0]], t[outs[0]]
+                dst[...] = tf_oracle.prefix_sum(src, src.ndim - 1 - params[0]).reshape(dst.shape)
+            elif op == "sort":
+                keys = t[ins[0]]
+                values = t[ins[1]] if params[0] else None
+                k, v = tf_oracle.radix_sort(keys.reshape(-1), None if values is None else values.reshape(-1), max_bits=params[1])
+                t[outs[0]][...] = k.reshape(t[outs[0]].shape)
+                if values is not None:
+                    t[outs[1]][...] = v.reshape(t[outs[1]].shape)
+            else:
+                return -1
+            return 1
+        except Exception as e:  # noqa: BLE001
+            print(f"[run_sim] library call {calls.get(kernel_id)} failed: {type(e).__name__}: {e}", file=sys.stderr, flush=True)
+            return -1
+    return callback
+
+
+LIBRARY_CB = C.CFUNCTYPE(C.c_int, C.c_size_t, C.c_size_t, C.POINTER(SimTensor))
+
+
 def build(host_code, kernels, tag):
     """g++ the two translation units (emitted kernels through the shim; generated host program + sim runtime) into one library."""
     work = tempfile.mkdtemp(prefix=f"tfsim_{tag}_")
@@ -144,6 +209,11 @@ def build(host_code, kernels, tag):
     lib.sim_run.restype = C.c_int
     lib.sim_error.restype = C.c_char_p
     lib.sim_free.argtypes = [C.c_void_p]
+    calls = library_calls(kernels)
+    if calls:
+        lib._library_cb = LIBRARY_CB(make_library_callback(calls))  # keep the thunk alive with the library
+        lib.sim_set_library_callback.argtypes = [LIBRARY_CB]
+        lib.sim_set_library_callback(lib._library_cb)
     return lib
 
 
@@ -180,7 +250,6 @@ class HostTensor:
 
 def main():
     out_path, specs = sys.argv[1], sys.argv[2:]
-    os.environ["TFCUDA_LIBRARY"] = "0"
     import tensorfrost_b200
     from tensorfrost_b200 import workloads
     tf = tensorfrost_b200.import_module()
@@ -203,6 +272,10 @@ def main():
         seen = 0
         for spec in specs:
             parts = spec.split(":")
+            # a trailing ":library" traces the case with the library lowerings on (marker kernels computed by the library callback)
+            os.environ["TFCUDA_LIBRARY"] = "1" if parts[-1] == "library" else "0"
+            if parts[-1] == "library":
+                parts = parts[:-1]
             name = parts[0]
             del captured[:]
             if name == "fluid":

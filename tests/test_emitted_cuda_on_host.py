@@ -19,6 +19,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 GOLDEN = os.path.join(HERE, "golden")
 FLUID_NAMES = ["vx", "vy", "pressure", "density", "div", "canvas"]
+# cases whose programs change under the library lowering (tests/test_parity_gpu.py USES_LIBRARY + the weight-gradient case)
+LIBRARY_CASES = ["row_reductions", "int_reductions", "prefix_sum", "sort_radix_u32", "sort_radix_f32", "sort_radix_i32", "matmul", "qr_inverse",
+                 "autograd_mlp", "autograd_batched_dense"]
 
 
 def _golden(name):
@@ -45,7 +48,8 @@ def test_emitted_kernels_reproduce_the_reference_on_the_host(tmp_path):
     fluid = np.load(os.path.join(GOLDEN, "fluid_128.npz"))
     fluid_spec = f"fluid:{int(fluid['n'])}:{int(fluid['n'])}:{int(fluid['steps'])}"
     out = str(tmp_path / "sim.npz")
-    r = subprocess.run([sys.executable, os.path.join(HERE, "cpu_sim", "run_sim.py"), out] + list(specs.values()) + [fluid_spec, "nca"],
+    library_specs = {n: specs[n] + ":library" for n in LIBRARY_CASES}
+    r = subprocess.run([sys.executable, os.path.join(HERE, "cpu_sim", "run_sim.py"), out] + list(specs.values()) + [fluid_spec, "nca"] + list(library_specs.values()),
                        cwd=str(tmp_path), capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0, r.stderr[-3000:]
     got = np.load(out)
@@ -55,6 +59,12 @@ def test_emitted_kernels_reproduce_the_reference_on_the_host(tmp_path):
         have = [got[f"{specs[n]}/{k}"] for k in range(len(want))]
         cases.compare(cases.CASES[n], have, want)
         exact += all(np.array_equal(np.ascontiguousarray(a).view(np.uint8), np.ascontiguousarray(b).view(np.uint8)) for a, b in zip(have, want))
+    # the same programs traced with the LIBRARY lowering: marker kernels, role -> binding maps, axis conventions, the sort call without a
+    # scratch tensor, the matmul VJP rewritten as one contraction (tfcuda_matmul_tn) - with the numpy restatement standing in for the
+    # hand-written kernels, so this pins the lowering's structure and arithmetic, not the kernels (those are GPU tests)
+    for n in LIBRARY_CASES:
+        _, _, want = _golden(n)
+        cases.compare(cases.CASES[n], [got[f"{library_specs[n]}/{k}"] for k in range(len(want))], want)
     for k, name in enumerate(FLUID_NAMES):
         a, b = got[f"{fluid_spec}/{k}"].astype(np.float64), fluid[name].astype(np.float64)
         assert np.abs(a - b).max() <= 1e-6 * np.abs(b).max(), f"fluid {name}"
