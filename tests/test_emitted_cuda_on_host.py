@@ -49,7 +49,7 @@ def test_emitted_kernels_reproduce_the_reference_on_the_host(tmp_path):
     fluid_spec = f"fluid:{int(fluid['n'])}:{int(fluid['n'])}:{int(fluid['steps'])}"
     out = str(tmp_path / "sim.npz")
     library_specs = {n: specs[n] + ":library" for n in LIBRARY_CASES}
-    r = subprocess.run([sys.executable, os.path.join(HERE, "cpu_sim", "run_sim.py"), out] + list(specs.values()) + [fluid_spec, "nca"] + list(library_specs.values()),
+    r = subprocess.run([sys.executable, os.path.join(HERE, "cpu_sim", "run_sim.py"), out] + list(specs.values()) + [fluid_spec, "nca", "nca:library"] + list(library_specs.values()),
                        cwd=str(tmp_path), capture_output=True, text=True, timeout=1200)
     assert r.returncode == 0, r.stderr[-3000:]
     got = np.load(out)
@@ -71,11 +71,13 @@ def test_emitted_kernels_reproduce_the_reference_on_the_host(tmp_path):
     # the grad program of the data-parallel NCA step (83 emitted kernels: 3 CA steps, autodiff, float atomics, and the reference's
     # out-of-range neighbour read, which the zero guard bands make deterministic) against the reference's gradients, loss and state
     nca = np.load(os.path.join(GOLDEN, "nca_step.npz"))
-    flat, state = got["nca/2"], got["nca/3"]
-    assert flat.shape == nca["flat0"].shape
     scale = np.abs(nca["flat0"][:-1]).max()
-    assert np.abs(flat[:-1].astype(np.float64) - nca["flat0"][:-1]).max() <= 1e-5 * scale
-    assert abs(float(flat[-1]) - float(nca["split_losses"][0])) <= 1e-6
-    assert np.abs(state - nca["state0"]).max() <= 2.0 / 255.0 + 1e-6 and np.mean(np.abs(state - nca["state0"]) > 1e-6) < 0.02
+    for spec in ("nca", "nca:library"):  # generic lowering; library lowering (matmul / matmul_tn / reduce calls behind the numpy stand-ins)
+        flat, state = got[f"{spec}/2"], got[f"{spec}/3"]
+        assert flat.shape == nca["flat0"].shape
+        assert np.abs(flat[:-1].astype(np.float64) - nca["flat0"][:-1]).max() <= 1e-5 * scale, spec
+        assert abs(float(flat[-1]) - float(nca["split_losses"][0])) <= 1e-6, spec
+        assert np.abs(state - nca["state0"]).max() <= 2.0 / 255.0 + 1e-6 and np.mean(np.abs(state - nca["state0"]) > 1e-6) < 0.02, spec
+    flat = got["nca/2"]
     print(f"{exact} of {len(names)} cases bit-identical to the reference; NCA gradients max |diff| "
           f"{np.abs(flat[:-1].astype(np.float64) - nca['flat0'][:-1]).max():.1e}")
