@@ -81,3 +81,31 @@ def test_emitted_kernels_reproduce_the_reference_on_the_host(tmp_path):
     flat = got["nca/2"]
     print(f"{exact} of {len(names)} cases bit-identical to the reference; NCA gradients max |diff| "
           f"{np.abs(flat[:-1].astype(np.float64) - nca['flat0'][:-1]).max():.1e}")
+
+
+ODD_SPECS = ["wave:37:3", "wave:1:4", "math_ops:1:5", "math_ops:257:6", "int_ops:33:7", "prefix_sum:1000:8", "atomics:777:9", "reshape_reduce:3:10",
+             "control_flow:130:11", "split_merge:8:12", "host_loop:17:13", "nbody:65:14", "matmul:33:15", "int_reductions:7:16"]
+
+
+def test_emitted_kernels_match_a_live_reference_run_at_odd_sizes(tmp_path):
+    """Sizes that are not multiples of the block shape (tail guards, one-element tensors, partial last blocks) and other seeds than the
+    fixtures: the reference itself (oracle/_ref, strict flags) and the host execution of the emitted CUDA text, same seeded inputs."""
+    import tensorfrost_b200
+    try:
+        tensorfrost_b200.module_path()
+    except ImportError:
+        pytest.skip("CUDA-enabled module not built here")
+    if not os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "TensorFrost")):
+        pytest.skip("oracle/_ref (the reference module) is not built here")
+    ref, sim = str(tmp_path / "ref.npz"), str(tmp_path / "sim.npz")
+    for cmd in ([sys.executable, os.path.join(HERE, "run_case.py"), "cpu", ref] + ODD_SPECS,
+                [sys.executable, os.path.join(HERE, "cpu_sim", "run_sim.py"), sim] + ODD_SPECS):
+        r = subprocess.run(cmd, cwd=str(tmp_path), capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stderr[-3000:]
+    want_all, got_all = np.load(ref), np.load(sim)
+    for spec in ODD_SPECS:
+        want = []
+        while f"{spec}/{len(want)}" in want_all:
+            want.append(want_all[f"{spec}/{len(want)}"])
+        assert want, spec
+        cases.compare(cases.CASES[spec.split(":")[0]], [got_all[f"{spec}/{k}"] for k in range(len(want))], want)
