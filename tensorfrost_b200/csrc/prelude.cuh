@@ -32,6 +32,8 @@ typedef unsigned int uint;
 // (the 32 multigrid sweeps of the fluid step: 3.6 us each for 3 MB of L2-resident data).
 #ifndef TF_HOST_SIM  // tests/cpu_sim runs the emitted text on the host, where this PTX does not exist
 TF_DEV void tf_pdl_prologue() { asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory"); }
+#else
+TF_DEV void tf_pdl_prologue() {}
 #endif
 
 // ---- bit casts (CPP.cpp:53-96) ------------------------------------------------------------
