@@ -304,23 +304,38 @@ def main():
                 g = np.load(os.path.join(TESTS, "golden", "nca_step.npz"))
                 batch, grid, pool_size, steps = int(g["global_batch"]), int(g["grid"]), int(g["pool_size"]), int(g["train_steps"])
                 nca = workloads.load_nca(tf, batch, grid, pool_size=pool_size, train_steps=steps, channel_n=12)
-                grad_step, _apply, _mono, shapes = nca_dp.build_programs(tf, nca, steps)
+                grad_step, apply_step, _mono, shapes = nca_dp.build_programs(tf, nca, steps)
                 program = tf.compile(grad_step)
                 kernels = tf.get_all_generated_kernels()[seen:]
                 seen += len(kernels)
+                apply_program = tf.compile(apply_step)
+                apply_kernels = tf.get_all_generated_kernels()[seen:]
+                seen += len(apply_kernels)
                 rng = np.random.default_rng(0)
                 hidden = 128
                 fc1 = (rng.standard_normal((48, hidden)) * np.sqrt(2.0 / 48)).astype(np.float32)
                 zeros = lambda *sh: np.zeros(sh, np.float32)  # noqa: E731
                 trainable = [fc1, zeros(hidden), zeros(hidden, 12), zeros(12)]
-                # input order of the traced program (its check_tensor lines): model parameters, filters, seed, Adam t, m[4], v[4], pool, image
-                inputs = trainable + [workloads.nca_filters(), np.array([0], np.uint32), zeros(1)] + [np.zeros_like(t) for t in trainable] \
-                    + [np.zeros_like(t) for t in trainable] + [workloads.nca_pool(pool_size, grid, 12), workloads.nca_target(grid, 0),
-                                                               np.asarray(g["ids"], np.int32), np.array([float(nca.CELL_FIRE_RATE)], np.float32)]
-                print(f"[run_sim] nca grad program: {len(kernels)} kernels", file=sys.stderr, flush=True)
-                outs = run(build(program.compiled_code(), kernels, "nca"), inputs, 4, "nca")
-                for k, o in enumerate(outs):
+                # optimizer module parameters in the order both traced programs declare them (their check_tensor lines):
+                # fc1, fc1_bias, fc2, fc2_bias, filters, seed, Adam t, m[4], v[4]  (t, m, v start at zero: optimizers.py:55-63)
+                opt = trainable + [workloads.nca_filters(), np.array([0], np.uint32), zeros(1)] + [np.zeros_like(t) for t in trainable] \
+                    + [np.zeros_like(t) for t in trainable]
+                pool, image = workloads.nca_pool(pool_size, grid, 12), workloads.nca_target(grid, 0)
+                ids, fire, lr = np.asarray(g["ids"], np.int32), np.array([float(nca.CELL_FIRE_RATE)], np.float32), np.array([float(g["lr"])], np.float32)
+                print(f"[run_sim] nca: grad program {len(kernels)} kernels, apply program {len(apply_kernels)} kernels", file=sys.stderr, flush=True)
+                grad_lib, apply_lib = build(program.compiled_code(), kernels, "nca_grad"), build(apply_program.compiled_code(), apply_kernels, "nca_apply")
+                losses = []
+                first = None
+                for _ in range(len(g["split_losses"])):  # NcaTrainer.step: grad program -> (exchange) -> apply program
+                    pool, seed, flat, state = run(grad_lib, opt + [pool, image, ids, fire], 4, "nca_grad")
+                    opt[5] = seed
+                    if first is None:
+                        first = (pool, seed, flat, state)
+                    losses.append(float(flat[-1]))
+                    opt = run(apply_lib, opt + [flat, lr], 15, "nca_apply")
+                for k, o in enumerate(first):
                     result[f"{spec}/{k}"] = o
+                result[f"{spec}/losses"] = np.array(losses, np.float64)
                 continue
             size = int(parts[1]) if len(parts) > 1 and parts[1] else None
             seed = int(parts[2]) if len(parts) > 2 else 0

@@ -68,8 +68,9 @@ def test_emitted_kernels_reproduce_the_reference_on_the_host(tmp_path):
     for k, name in enumerate(FLUID_NAMES):
         a, b = got[f"{fluid_spec}/{k}"].astype(np.float64), fluid[name].astype(np.float64)
         assert np.abs(a - b).max() <= 1e-6 * np.abs(b).max(), f"fluid {name}"
-    # the grad program of the data-parallel NCA step (83 emitted kernels: 3 CA steps, autodiff, float atomics, and the reference's
-    # out-of-range neighbour read, which the zero guard bands make deterministic) against the reference's gradients, loss and state
+    # the two programs of the data-parallel NCA step (grad: 83 emitted kernels - 3 CA steps, autodiff, float atomics, and the reference's
+    # out-of-range neighbour read, which the zero guard bands make deterministic; apply: 11 kernels) against the reference's gradients,
+    # loss, state and 3-iteration loss sequence
     nca = np.load(os.path.join(GOLDEN, "nca_step.npz"))
     scale = np.abs(nca["flat0"][:-1]).max()
     for spec in ("nca", "nca:library"):  # generic lowering; library lowering (matmul / matmul_tn / reduce calls behind the numpy stand-ins)
@@ -78,6 +79,8 @@ def test_emitted_kernels_reproduce_the_reference_on_the_host(tmp_path):
         assert np.abs(flat[:-1].astype(np.float64) - nca["flat0"][:-1]).max() <= 1e-5 * scale, spec
         assert abs(float(flat[-1]) - float(nca["split_losses"][0])) <= 1e-6, spec
         assert np.abs(state - nca["state0"]).max() <= 2.0 / 255.0 + 1e-6 and np.mean(np.abs(state - nca["state0"]) > 1e-6) < 0.02, spec
+        # three whole training iterations (grad program -> apply program with norm clipping + Adam -> next grad program): the loss sequence
+        np.testing.assert_allclose(got[f"{spec}/losses"], nca["split_losses"], rtol=1e-5, err_msg=spec)
     flat = got["nca/2"]
     print(f"{exact} of {len(names)} cases bit-identical to the reference; NCA gradients max |diff| "
           f"{np.abs(flat[:-1].astype(np.float64) - nca['flat0'][:-1]).max():.1e}")
