@@ -12,9 +12,11 @@
 // (a tile of whole rows is one contiguous block: coalesced 128-bit loads, no transpose), and the products are plain fp32 FFMA in
 // the reference's k order (Compiler/Implementations.cpp:560-646) - bit-compatible with the oracle up to FMA contraction, no TF32.
 // Bound: fp32 FFMA issue (2*K*N flop per row against 4*(K+N) bytes).
+#ifndef TF_HOST_SIM  // tests/cpu_sim/kernel_on_host.cpp compiles the kernel below for the host through cuda_host_shim.h
 #include <algorithm>
 
 #include "tfcuda_internal.h"
+#endif
 
 namespace {
 
@@ -147,6 +149,7 @@ __global__ void __launch_bounds__(MR_THREADS) matmul_rows_kernel(const float* __
 	}
 }
 
+#ifndef TF_HOST_SIM
 template <int TXN, int CH, int TM>
 int launch_rows(const float* a, const float* b, float* c, size_t r, size_t k, size_t n) {
 	tfcuda::State& s = tfcuda::state();
@@ -171,8 +174,11 @@ int launch_rows(const float* a, const float* b, float* c, size_t r, size_t k, si
 	return tfcuda::check_launch("matmul_rows_kernel");
 }
 
+#endif  // TF_HOST_SIM
+
 }  // namespace
 
+#ifndef TF_HOST_SIM
 extern "C" int tfcuda_matmul_rows_supported(size_t r, size_t k, size_t n) {
 	if (r == 0 || k == 0 || n == 0 || n > 128 || k > 0x7fff) return 0;
 	const size_t bn = n <= 16 ? 16 : n <= 32 ? 32 : n <= 64 ? 64 : 128;
@@ -194,3 +200,4 @@ extern "C" int tfcuda_matmul_rows(uint64_t a, uint64_t b, uint64_t c, size_t r, 
 	if (n <= 64) return launch_rows<16, 1, 4>(pa, pb, pc, r, k, n);   // BN 64,  BR 64
 	return launch_rows<16, 2, 4>(pa, pb, pc, r, k, n);                // BN 128, BR 64
 }
+#endif  // TF_HOST_SIM

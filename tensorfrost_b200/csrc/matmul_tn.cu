@@ -10,9 +10,11 @@
 //   * the contraction is split over gridDim.y CTAs (split-K, R is 10^6 while M*N is one or two tiles), each writes its partial
 //     tile to a workspace, and a second kernel adds the partials in a fixed order: deterministic, no float atomics.
 // Bound: fp32 FFMA issue (2*R*M*N flop against 4*R*(M+N) bytes is ~18 flop/byte at 48 x 128, above the FFMA/HBM balance point).
+#ifndef TF_HOST_SIM  // tests/cpu_sim/kernel_on_host.cpp compiles the kernels below for the host through cuda_host_shim.h
 #include <algorithm>
 
 #include "tfcuda_internal.h"
+#endif
 
 namespace {
 
@@ -159,6 +161,7 @@ __global__ void __launch_bounds__(256) matmul_tn_reduce_kernel(const float* __re
 	c[i] = (s0 + s1) + (s2 + s3);
 }
 
+#ifndef TF_HOST_SIM
 template <int BM, int BN, int TM, int TN>
 int launch_tn(const float* a, const float* b, float* c, size_t r, size_t m, size_t n) {
 	tfcuda::State& s = tfcuda::state();
@@ -188,8 +191,11 @@ int launch_tn(const float* a, const float* b, float* c, size_t r, size_t m, size
 	return 0;
 }
 
+#endif  // TF_HOST_SIM
+
 }  // namespace
 
+#ifndef TF_HOST_SIM
 extern "C" int tfcuda_matmul_tn(uint64_t a, uint64_t b, uint64_t c, size_t r, size_t m, size_t n) {
 	tfcuda::State& s = tfcuda::state();
 	if (!s.initialized) { tfcuda::set_error("tfcuda_matmul_tn: not initialised"); return 1; }
@@ -204,3 +210,4 @@ extern "C" int tfcuda_matmul_tn(uint64_t a, uint64_t b, uint64_t c, size_t r, si
 	if (n <= 32) return launch_tn<128, 32, 8, 4>(pa, pb, pc, r, m, n);
 	return launch_tn<64, 128, 8, 8>(pa, pb, pc, r, m, n);
 }
+#endif  // TF_HOST_SIM

@@ -1,0 +1,129 @@
+// TEST INFRASTRUCTURE ONLY.  Compiles hand-written CUDA kernels of tensorfrost_b200/csrc for the HOST through cuda_host_shim.h and runs
+// them with one host thread per CUDA thread of a block (blocks one after the other, __syncthreads = std::barrier), against a float64
+// reference.  Used for kernels written when no GPU was available (matmul_rows.cu, never run on hardware in round 1); matmul_tn.cu, which
+// IS validated on hardware, runs through the same harness as its control.  Checks the kernels' logic - staging, synchronisation
+// structure, index arithmetic, tails - not their speed and not the hardware.
+//   g++ -std=c++20 -O2 -pthread -I tests/cpu_sim -I tensorfrost_b200/csrc tests/cpu_sim/kernel_on_host.cpp -o kernel_on_host && ./kernel_on_host
+#include "cuda_host_shim.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <functional>
+#include <random>
+
+using std::max;
+using std::min;
+
+struct float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+template <typename T> static inline T __ldg(const T* p) { return *p; }
+#define __align__(n) __attribute__((aligned(n)))
+
+// matmul_tn.cu declares fixed-size __shared__ arrays inside its kernel: statics shared by the block's threads (the shim's default)
+#include "matmul_tn.cu"
+
+// matmul_rows.cu uses dynamic shared memory: `extern __shared__ float smem[]` becomes a reference to this buffer
+#undef __shared__
+#define __shared__
+namespace { alignas(16) float smem[64 * 1024]; }  // the kernel sits in an anonymous namespace: its `extern` declaration resolves here
+#include "matmul_rows.cu"
+
+// one block after the other; the threads of a block concurrently, around a barrier
+static void launch(unsigned grid_x, unsigned grid_y, unsigned threads, const std::function<void()>& kernel) {
+	for (unsigned by = 0; by < grid_y; by++)
+		for (unsigned bx = 0; bx < grid_x; bx++) {
+			std::barrier<> bar(threads);
+			sim_block_barrier = &bar;
+			std::vector<std::thread> pool;
+			for (unsigned t = 0; t < threads; t++)
+				pool.emplace_back([&, t]() {
+					gridDim = sim_dim3{grid_x, grid_y, 1};
+					blockDim = sim_dim3{threads, 1, 1};
+					blockIdx = sim_dim3{bx, by, 0};
+					threadIdx = sim_dim3{t, 0, 0};
+					kernel();
+					bar.arrive_and_drop();
+				});
+			for (auto& th : pool) th.join();
+			sim_block_barrier = nullptr;
+		}
+}
+
+static std::vector<float> random_matrix(size_t n, unsigned seed) {
+	std::mt19937 rng(seed);
+	std::normal_distribution<float> dist(0.0f, 1.0f);
+	std::vector<float> v(n);
+	for (auto& x : v) x = dist(rng);
+	return v;
+}
+
+static double max_rel_err(const std::vector<float>& got, const std::vector<double>& want) {
+	double scale = 1e-30, err = 0;
+	for (double w : want) scale = std::max(scale, std::fabs(w));
+	for (size_t i = 0; i < want.size(); i++) {
+		if (!(got[i] == got[i])) return 1e30;  // NaN: an element was never written
+		err = std::max(err, std::fabs((double)got[i] - want[i]));
+	}
+	return err / scale;
+}
+
+template <int TXN, int CH, int TM>
+static bool check_rows(size_t r, size_t k, size_t n, unsigned grid) {
+	constexpr int BR = (MR_THREADS / TXN) * TM;
+	auto a = random_matrix(r * k, (unsigned)(r + k)), b = random_matrix(k * n, (unsigned)(k + n));
+	std::vector<float> c(r * n, std::nanf(""));
+	std::vector<double> want(r * n, 0.0);
+	for (size_t i = 0; i < r; i++)
+		for (size_t kk = 0; kk < k; kk++)
+			for (size_t j = 0; j < n; j++) want[i * n + j] += (double)a[i * k + kk] * (double)b[kk * n + j];
+	const long long tiles = (long long)((r + BR - 1) / BR);
+	launch(std::min<unsigned>(grid, (unsigned)tiles), 1, MR_THREADS, [&]() { matmul_rows_kernel<TXN, CH, TM>(a.data(), b.data(), c.data(), (long long)r, (int)k, (int)n, tiles); });
+	double e = max_rel_err(c, want);
+	std::printf("matmul_rows<%d,%d,%d> R=%zu K=%zu N=%zu grid=%u: max rel err %.2e %s\n", TXN, CH, TM, r, k, n, grid, e, e <= 2e-6 ? "ok" : "FAIL");
+	return e <= 2e-6;
+}
+
+template <int BM, int BN, int TM, int TN>
+static bool check_tn(size_t r, size_t m, size_t n, long splits) {
+	auto a = random_matrix(r * m, (unsigned)(r + m)), b = random_matrix(r * n, (unsigned)(r + n));
+	std::vector<double> want(m * n, 0.0);
+	for (size_t i = 0; i < r; i++)
+		for (size_t x = 0; x < m; x++)
+			for (size_t y = 0; y < n; y++) want[x * n + y] += (double)a[i * m + x] * (double)b[i * n + y];
+	long long rows_per_split = (long long)((r + splits - 1) / splits);
+	rows_per_split = (rows_per_split + TN_BR - 1) / TN_BR * TN_BR;
+	splits = (long)((r + rows_per_split - 1) / rows_per_split);
+	const int tiles_m = (int)((m + BM - 1) / BM), tiles_n = (int)((n + BN - 1) / BN);
+	std::vector<float> partial((size_t)splits * m * n, std::nanf("")), c(m * n, std::nanf(""));
+	const bool vec = (m % 4 == 0) && (n % 4 == 0);
+	constexpr int threads = (BM / TM) * (BN / TN);
+	launch((unsigned)(tiles_m * tiles_n), (unsigned)splits, threads, [&]() {
+		if (vec) matmul_tn_kernel<BM, BN, TM, TN, true>(a.data(), b.data(), partial.data(), (long long)r, (int)m, (int)n, rows_per_split, tiles_n);
+		else matmul_tn_kernel<BM, BN, TM, TN, false>(a.data(), b.data(), partial.data(), (long long)r, (int)m, (int)n, rows_per_split, tiles_n);
+	});
+	const int mn = (int)(m * n);
+	launch((unsigned)((mn + 255) / 256), 1, 256, [&]() { matmul_tn_reduce_kernel(partial.data(), c.data(), mn, (int)splits); });
+	double e = max_rel_err(c, want);
+	std::printf("matmul_tn<%d,%d,%d,%d> R=%zu M=%zu N=%zu splits=%ld: max rel err %.2e %s\n", BM, BN, TM, TN, r, m, n, splits, e, e <= 2e-6 ? "ok" : "FAIL");
+	return e <= 2e-6;
+}
+
+int main() {
+	bool ok = true;
+	// control: the hardware-validated weight-gradient kernel through the same harness
+	ok &= check_tn<64, 128, 8, 8>(1000, 48, 128, 5);
+	ok &= check_tn<128, 16, 8, 2>(777, 128, 12, 3);
+	ok &= check_tn<128, 32, 8, 4>(300, 20, 24, 2);
+	// the skinny matmul written without a GPU: every template configuration the dispatcher uses, NCA's four shapes, ragged tails
+	ok &= check_rows<16, 2, 4>(200, 48, 128, 2);    // fc1 forward: K = 48 (two chunks: 32 + 16), BN 128
+	ok &= check_rows<4, 1, 4>(600, 128, 12, 2);     // fc2 forward: K = 128 (four chunks), N = 12 in a 16-wide tile
+	ok &= check_rows<16, 2, 4>(130, 12, 128, 3);    // dX2: K = 12 (one short chunk)
+	ok &= check_rows<16, 1, 4>(100, 128, 48, 1);    // dX1: N = 48 in a 64-wide tile
+	ok &= check_rows<8, 1, 4>(257, 36, 30, 2);      // BN 32, N not a multiple of 4 (scalar stores), ragged last tile
+	ok &= check_rows<4, 1, 4>(300, 7, 5, 1);        // K not a multiple of 4: scalar A loads, zero-padded k
+	ok &= check_rows<16, 2, 4>(1, 4, 128, 4);       // one row, more CTAs than tiles
+	std::printf(ok ? "ALL OK\n" : "SOME FAILED\n");
+	return ok ? 0 : 1;
+}
