@@ -9,9 +9,11 @@
 // (X is 3 MB at N=262144 and stays in L2), not HBM and not tensor cores.
 // The sum over j is per-thread serial in j order like the oracle's loop; -dx/(d2*sqrt(d2)) is evaluated as
 // -dx * rsqrt(d2)^3, a few ulp from the oracle's divide (tests bound the step at 1e-5 relative).
+#ifndef TF_HOST_SIM  // tests/cpu_sim/kernel_on_host.cpp compiles the kernels below for the host through cuda_host_shim.h
 #include <cstdlib>
 
 #include "tfcuda_internal.h"
+#endif
 
 namespace {
 
@@ -19,11 +21,15 @@ constexpr int NB_THREADS = 128;
 constexpr int NB_PER_THREAD = 2;
 constexpr int NB_TILE = 256;  // j bodies per shared-memory stage
 
+#ifndef TF_HOST_SIM
 __device__ __forceinline__ float fast_rsqrt(float v) {
 	float r;
 	asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
 	return r;
 }
+#else
+static inline float fast_rsqrt(float v) { return 1.0f / sqrtf(v); }  // host stand-in (the hardware instruction is 2 ulp from this)
+#endif
 
 __global__ void __launch_bounds__(NB_THREADS) nbody_kernel(const float* __restrict__ x, const float* __restrict__ v, float* __restrict__ x_new,
                                                            float* __restrict__ v_new, int n, float dt, float eps) {
@@ -97,11 +103,23 @@ __global__ void __launch_bounds__(NB_THREADS) nbody_kernel(const float* __restri
 // each f32x2 instruction works on a (j, j+1) pair: per pair and i body 3 sub2 + 3 fma2 + 2 mul2 + 3 fma2 = 11 issue slots + 2 MUFU,
 // i.e. 6.5 slots per interaction against 12 for the scalar loop.  Even and odd j's accumulate separately and are added at the end.
 typedef unsigned long long u64;
+#ifndef TF_HOST_SIM
 __device__ __forceinline__ u64 pack2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 __device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+#else  // host stand-ins with the same lane layout (low word = first lane) and the same IEEE operations per lane
+static inline u64 pack2(float lo, float hi) { return (u64)__float_as_uint(lo) | ((u64)__float_as_uint(hi) << 32); }
+static inline void unpack2(u64 v, float& lo, float& hi) { lo = __uint_as_float((unsigned)v); hi = __uint_as_float((unsigned)(v >> 32)); }
+static inline u64 sub2(u64 a, u64 b) { float al, ah, bl, bh; unpack2(a, al, ah); unpack2(b, bl, bh); return pack2(al - bl, ah - bh); }
+static inline u64 mul2(u64 a, u64 b) { float al, ah, bl, bh; unpack2(a, al, ah); unpack2(b, bl, bh); return pack2(al * bl, ah * bh); }
+static inline u64 fma2(u64 a, u64 b, u64 c) {
+	float al, ah, bl, bh, cl, ch;
+	unpack2(a, al, ah); unpack2(b, bl, bh); unpack2(c, cl, ch);
+	return pack2(fmaf(al, bl, cl), fmaf(ah, bh, ch));
+}
+#endif
 
 constexpr int NX_THREADS = 128;
 constexpr int NX_TILE = 512;  // j bodies per stage (SoA: 3 x 2 KB)
@@ -170,6 +188,7 @@ __global__ void __launch_bounds__(NX_THREADS) nbody_kernel_x2(const float* __res
 
 }  // namespace
 
+#ifndef TF_HOST_SIM
 extern "C" int tfcuda_nbody_step(uint64_t x, uint64_t v, uint64_t x_new, uint64_t v_new, size_t n, float dt, float eps) {
 	tfcuda::State& s = tfcuda::state();
 	if (!s.initialized) { tfcuda::set_error("tfcuda_nbody_step: not initialised"); return 1; }
@@ -186,3 +205,4 @@ extern "C" int tfcuda_nbody_step(uint64_t x, uint64_t v, uint64_t x_new, uint64_
 		                                                  reinterpret_cast<float*>(v_new), (int)n, dt, eps);
 	return tfcuda::check_launch("tfcuda_nbody_step");
 }
+#endif  // TF_HOST_SIM

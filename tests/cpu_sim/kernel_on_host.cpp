@@ -24,6 +24,10 @@ template <typename T> static inline T __ldg(const T* p) { return *p; }
 // matmul_tn.cu declares fixed-size __shared__ arrays inside its kernel: statics shared by the block's threads (the shim's default)
 #include "matmul_tn.cu"
 
+// nbody.cu: fixed-size __shared__ tiles too; its PTX wrappers (rsqrt.approx, the packed f32x2 arithmetic) have host stand-ins in the file
+struct alignas(16) ulonglong2 { unsigned long long x, y; };
+#include "nbody.cu"
+
 // matmul_rows.cu uses dynamic shared memory: `extern __shared__ float smem[]` becomes a reference to this buffer
 #undef __shared__
 #define __shared__
@@ -110,8 +114,45 @@ static bool check_tn(size_t r, size_t m, size_t n, long splits) {
 	return e <= 2e-6;
 }
 
+// one gravity step: both kernels (scalar loop; packed f32x2 loop with its padded tail tile) against a float64 evaluation of the same formula
+static bool check_nbody(int n, bool packed) {
+	auto x = random_matrix((size_t)n * 3, (unsigned)n);
+	for (auto& e : x) e *= 5.0f;
+	auto v = random_matrix((size_t)n * 3, (unsigned)n + 1);
+	for (auto& e : v) e *= 0.1f;
+	std::vector<float> xn((size_t)n * 3, std::nanf("")), vn((size_t)n * 3, std::nanf(""));
+	const float dt = 0.001f, eps = 1e-4f;
+	std::vector<double> want_v((size_t)n * 3), want_x((size_t)n * 3);
+	for (int i = 0; i < n; i++) {
+		double f[3] = {0, 0, 0};
+		for (int j = 0; j < n; j++) {
+			double d[3] = {(double)x[3 * i] - x[3 * j], (double)x[3 * i + 1] - x[3 * j + 1], (double)x[3 * i + 2] - x[3 * j + 2]};
+			double d2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2] + eps;
+			double w = 1.0 / (d2 * std::sqrt(d2));
+			for (int c = 0; c < 3; c++) f[c] -= d[c] * w;
+		}
+		for (int c = 0; c < 3; c++) {
+			want_v[3 * i + c] = v[3 * i + c] + f[c] * dt;
+			want_x[3 * i + c] = x[3 * i + c] + want_v[3 * i + c] * dt;
+		}
+	}
+	if (packed)
+		launch((unsigned)((n + NX_THREADS * 2 - 1) / (NX_THREADS * 2)), 1, NX_THREADS, [&]() { nbody_kernel_x2(x.data(), v.data(), xn.data(), vn.data(), n, dt, eps); });
+	else
+		launch((unsigned)((n + NB_THREADS * NB_PER_THREAD - 1) / (NB_THREADS * NB_PER_THREAD)), 1, NB_THREADS, [&]() { nbody_kernel(x.data(), v.data(), xn.data(), vn.data(), n, dt, eps); });
+	double ev = max_rel_err(vn, want_v), ex = max_rel_err(xn, want_x);
+	bool good = ev <= 1e-5 && ex <= 1e-6;
+	std::printf("nbody %s n=%d: v max rel err %.2e, x %.2e %s\n", packed ? "packed f32x2" : "scalar", n, ev, ex, good ? "ok" : "FAIL");
+	return good;
+}
+
 int main() {
 	bool ok = true;
+	// the n-body step: scalar kernel (validated on hardware through tests/test_library_gpu.py) and the packed kernel at the two sizes of
+	// tests/test_zy_late_gpu.py (5000 = nine full 512-body tiles + a padded tail)
+	ok &= check_nbody(1500, false);
+	ok &= check_nbody(4096, true);
+	ok &= check_nbody(5000, true);
 	// control: the hardware-validated weight-gradient kernel through the same harness
 	ok &= check_tn<64, 128, 8, 8>(1000, 48, 128, 5);
 	ok &= check_tn<128, 16, 8, 2>(777, 128, 12, 3);

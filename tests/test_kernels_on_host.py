@@ -3,7 +3,8 @@ CUDA thread of a block around a std::barrier (tests/cpu_sim/kernel_on_host.cpp),
 
 Subject: the skinny matmul of csrc/matmul_rows.cu, which was written after round 1's GPU budget ended and has never run on hardware -
 every template configuration its dispatcher uses, NCA's four shapes, ragged tails, scalar fallbacks.  Control: the weight-gradient
-kernel of csrc/matmul_tn.cu, which IS validated on hardware, through the same harness."""
+kernel of csrc/matmul_tn.cu, which IS validated on hardware, through the same harness.  Also the n-body step: the scalar kernel
+(hardware-validated) and the packed f32x2 kernel at the sizes of tests/test_zy_late_gpu.py, with host stand-ins for its PTX wrappers."""
 import os
 import subprocess
 
@@ -19,4 +20,4 @@ def test_hand_written_kernels_run_correctly_on_the_host(tmp_path):
     assert r.returncode == 0, r.stderr[-3000:]
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout[-3000:] + r.stderr[-1000:]
-    assert r.stdout.count(" ok") == 10 and "FAIL" not in r.stdout
+    assert r.stdout.count(" ok") == 13 and "FAIL" not in r.stdout
