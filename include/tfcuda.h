@@ -124,6 +124,18 @@ int tfcuda_buffer_read(const TFBuffer* buffer, size_t word_offset, uint32_t* dst
 int tfcuda_memcpy_h2d(uint64_t dst, const void* src, size_t bytes);
 int tfcuda_memcpy_d2h(void* dst, uint64_t src, size_t bytes);
 int tfcuda_memcpy_d2d(uint64_t dst, uint64_t src, size_t bytes);
+/* Copy engines (the fast path of PyTensorMemory upload/readback, Frontend/Python/PyTensorMemory.cpp:15-84, for pipelines): uploads
+ * and downloads run on their own streams so host->device, kernels and device->host overlap.  h2d_async starts once the work queued
+ * on the runtime stream so far is done (the previous users of dst); kernels queued after tfcuda_wait_uploads see the data.
+ * d2h_async starts once the work queued so far is done; the host may read dst after tfcuda_copy_sync.  Host memory should be
+ * page-locked (tfcuda_host_alloc); source / destination device memory must stay allocated until tfcuda_copy_sync. */
+int tfcuda_memcpy_h2d_async(uint64_t dst, const void* src, size_t bytes);
+int tfcuda_wait_uploads(void);
+int tfcuda_memcpy_d2h_async(void* dst, uint64_t src, size_t bytes);
+int tfcuda_copy_sync(void);
+/* downloads started / completed so far (a caller that owns the source buffers releases them once done >= its ticket) */
+uint64_t tfcuda_downloads_issued(void);
+uint64_t tfcuda_downloads_done(void);
 int tfcuda_memset32(uint64_t dst, uint32_t value, size_t words);
 uint64_t tfcuda_malloc(size_t bytes);   /* 0 on failure */
 int tfcuda_free(uint64_t ptr);
@@ -170,10 +182,32 @@ int tfcuda_nvrtc_check(const char* source, const char* options);
  * disk by source hash) and register them under their kernel ids.  options: extra NVRTC flags,
  * space separated (the reference's kernel_compile_options string, PybindModule.cpp:112-115). */
 int tfcuda_compile_kernels(const TFCudaKernelSource* kernels, size_t count, const char* options);
+/* Directory of the on-disk compile cache (cubins; the backend glue keeps compiled host programs there too, replacing the
+ * fixed /tmp/generated_lib_<id>.cpp of Backends/CPU/KernelCompiler.cpp:96-113).  $TFCUDA_CACHE_DIR, else $XDG_CACHE_HOME/tfcuda,
+ * else ~/.cache/tfcuda; must be owned by the calling user with mode 0700.  "" when the cache is disabled (TFCUDA_NO_CACHE set, or
+ * no safe directory). */
+const char* tfcuda_cache_dir(void);
 
 /* Launch by raw device pointers (mem[i] = device address of binding i). */
 int tfcuda_launch(size_t kernel_id, const uint64_t* mem, size_t n_mem,
                   const uint32_t* vars, size_t n_var, size_t work_group_count);
+/* Graph replay of a program's launches (whole-program CUDA graph).  The backend glue brackets every program execution
+ * (ExecuteProgram, Backend/Backend.cpp:137-185) with begin/end; in between tfcuda_launch only records, and the recorded chain is
+ * issued as ONE cudaGraphLaunch when the program ends or the moment anything else needs the stream (tf.read, a copy, a library
+ * kernel).  Executable graphs are cached by kernel sequence + argument bytes, so a steady-state step costs one graph launch.
+ * Bit-identical to eager execution; TFCUDA_GRAPH=0 disables it.  Calls nest; end returns non-zero when a deferred launch failed. */
+typedef struct TFCudaGraphStats {
+	int enabled;
+	uint64_t replays;         /* graph launches */
+	uint64_t exact_hits;      /* ... that reused an executable graph unchanged */
+	uint64_t patched;         /* ... whose kernel arguments were patched in place */
+	uint64_t instantiated;    /* ... that needed a new executable graph */
+	uint64_t eager_launches;  /* kernels of short chains launched one by one */
+} TFCudaGraphStats;
+int tfcuda_graph_begin(void);
+int tfcuda_graph_end(void);
+int tfcuda_graph_stats(TFCudaGraphStats* out);
+
 /* Launch from the reference's dispatch record (buffers must come from tfcuda_buffer_create). */
 int tfcuda_dispatch(const TFDispatchInfo* info);
 /* Counters: kernels launched since init (emitted + library), for bench.py's gpu_launches. */
@@ -259,6 +293,16 @@ int tfcuda_comm_unique_id(uint8_t out[128]);
 int tfcuda_comm_init(const uint8_t unique_id[128], int rank, int world);
 int tfcuda_comm_allreduce_sum_f32(uint64_t buf, size_t count, float scale);
 int tfcuda_comm_destroy(void);
+/* One-shot allreduce over NVLink peer memory for small payloads (<= tfcuda_peer_max_count() floats; the NCA exchange is 7821):
+ * every rank exports an exchange buffer (64-byte CUDA IPC handle, shared out of band like the NCCL id), maps its peers', and ONE
+ * kernel per step pushes the vector into every peer's buffer, waits for all peers' flags and sums in rank order (bit-identical
+ * result on every rank).  Same contract as tfcuda_comm_allreduce_sum_f32: in place on tfcuda_stream(), then multiplied by scale. */
+int tfcuda_peer_export(uint8_t handle_out[64]);
+int tfcuda_peer_init(const uint8_t* handles /* world x 64 bytes, rank order */, int rank, int world);
+int tfcuda_peer_ready(void);
+size_t tfcuda_peer_max_count(void);
+int tfcuda_peer_allreduce_sum_f32(uint64_t buf, size_t count, float scale);
+int tfcuda_peer_destroy(void);
 
 #ifdef __cplusplus
 }

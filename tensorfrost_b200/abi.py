@@ -3,7 +3,7 @@
 import ctypes as C
 import os
 
-from . import LIB_PATH
+from . import LIB_PATH, MODULE_DIR
 
 u64, sz, i32, u32, f32 = C.c_uint64, C.c_size_t, C.c_int, C.c_uint32, C.c_float
 TF_FLOAT, TF_UINT, TF_INT, TF_BOOL, TF_NONE = 0, 1, 2, 3, 4
@@ -38,6 +38,10 @@ class TFCudaKernelSource(C.Structure):
                 ("n_var", C.c_uint), ("library_op", C.c_uint)]
 
 
+class TFCudaGraphStats(C.Structure):
+    _fields_ = [("enabled", C.c_int), ("replays", u64), ("exact_hits", u64), ("patched", u64), ("instantiated", u64), ("eager_launches", u64)]
+
+
 class TFCudaProfileRecord(C.Structure):
     _fields_ = [("name", C.c_char * 64), ("launches", u64), ("total_ms", C.c_double), ("bytes", C.c_double)]
 
@@ -61,6 +65,12 @@ EXPORTS = {
     "tfcuda_memcpy_h2d": (i32, [u64, C.c_void_p, sz]),
     "tfcuda_memcpy_d2h": (i32, [C.c_void_p, u64, sz]),
     "tfcuda_memcpy_d2d": (i32, [u64, u64, sz]),
+    "tfcuda_memcpy_h2d_async": (i32, [u64, C.c_void_p, sz]),
+    "tfcuda_wait_uploads": (i32, []),
+    "tfcuda_memcpy_d2h_async": (i32, [C.c_void_p, u64, sz]),
+    "tfcuda_copy_sync": (i32, []),
+    "tfcuda_downloads_issued": (u64, []),
+    "tfcuda_downloads_done": (u64, []),
     "tfcuda_memset32": (i32, [u64, u32, sz]),
     "tfcuda_malloc": (u64, [sz]),
     "tfcuda_free": (i32, [u64]),
@@ -70,8 +80,12 @@ EXPORTS = {
     "tfcuda_prelude": (C.c_char_p, []),
     "tfcuda_nvrtc_check": (i32, [C.c_char_p, C.c_char_p]),
     "tfcuda_compile_kernels": (i32, [C.POINTER(TFCudaKernelSource), sz, C.c_char_p]),
+    "tfcuda_cache_dir": (C.c_char_p, []),
     "tfcuda_launch": (i32, [sz, C.POINTER(u64), sz, C.POINTER(u32), sz, sz]),
     "tfcuda_dispatch": (i32, [C.POINTER(TFDispatchInfo)]),
+    "tfcuda_graph_begin": (i32, []),
+    "tfcuda_graph_end": (i32, []),
+    "tfcuda_graph_stats": (i32, [C.POINTER(TFCudaGraphStats)]),
     "tfcuda_launch_count": (u64, []),
     "tfcuda_timer_begin": (i32, []),
     "tfcuda_timer_end": (i32, [C.POINTER(f32)]),
@@ -95,6 +109,12 @@ EXPORTS = {
     "tfcuda_comm_init": (i32, [C.c_void_p, i32, i32]),
     "tfcuda_comm_allreduce_sum_f32": (i32, [u64, sz, f32]),
     "tfcuda_comm_destroy": (i32, []),
+    "tfcuda_peer_export": (i32, [C.c_void_p]),
+    "tfcuda_peer_init": (i32, [C.c_void_p, i32, i32]),
+    "tfcuda_peer_ready": (i32, []),
+    "tfcuda_peer_max_count": (sz, []),
+    "tfcuda_peer_allreduce_sum_f32": (i32, [u64, sz, f32]),
+    "tfcuda_peer_destroy": (i32, []),
 }
 
 _lib = None
@@ -106,7 +126,13 @@ def lib():
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise OSError(f"{LIB_PATH} not built; run tensorfrost_b200/build_lib.sh — there is no fallback implementation")
-        l = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        # ONE runtime per process: the CUDA-enabled TensorFrost module resolves libtfcuda.so next to itself (RPATH $ORIGIN), so when
+        # that copy exists it is the file to open here too - the dynamic loader then maps a single library (one stream, one pool),
+        # whichever of the two is loaded first
+        beside_module = os.path.join(MODULE_DIR, "TensorFrost", "libtfcuda.so")
+        path = beside_module if os.path.exists(beside_module) else LIB_PATH
+        l = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        l.path = path
         for name, (res, args) in EXPORTS.items():
             fn = getattr(l, name)
             fn.restype = res

@@ -38,4 +38,6 @@ done
 for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
 "$NVCC" -shared -cudart static -o "$OUT/libtfcuda.so" "${objs[@]}" -L/usr/local/cuda/lib64 -lnvrtc -ldl -lpthread \
   -Xlinker -rpath -Xlinker /usr/local/cuda/lib64
+# the CUDA-enabled module loads the copy next to itself (RPATH $ORIGIN): keep it identical
+if [ -d "$HERE/../build/tf_cuda/TensorFrost" ]; then cp "$OUT/libtfcuda.so" "$HERE/../build/tf_cuda/TensorFrost/libtfcuda.so"; fi
 echo "[tfcuda] built $OUT/libtfcuda.so"

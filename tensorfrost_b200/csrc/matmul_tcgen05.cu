@@ -290,17 +290,21 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 	}
 }
 
-// hi = x with the 13 low mantissa bits cleared (exactly representable in tf32), lo = x - hi (exact in fp32)
+// hi = x with the 13 low mantissa bits cleared (exactly representable in tf32), lo = x - hi (exact in fp32).  For a non-finite x
+// (Inf - Inf would make lo NaN and poison whole rows where the reference's fp32 loop yields Inf) lo is 0.  The tensor core truncates lo
+// to 10 mantissa bits again, so the compensated product is accurate to ~2^-21 relative, not the full 2^-24 of an fp32 FMA chain.
+__device__ __forceinline__ float tf32_lo(float v, float h) { return (__float_as_uint(h) & 0x7f800000u) == 0x7f800000u ? 0.f : v - h; }
+
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, size_t n) {
 	const size_t stride = (size_t)gridDim.x * blockDim.x;
 	const size_t n4 = n >> 2;
 	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
 		float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
 		float4 h, l;
-		h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
-		h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
-		h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
-		h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+		h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = tf32_lo(v.x, h.x);
+		h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = tf32_lo(v.y, h.y);
+		h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = tf32_lo(v.z, h.z);
+		h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = tf32_lo(v.w, h.w);
 		reinterpret_cast<float4*>(hi)[i] = h;
 		reinterpret_cast<float4*>(lo)[i] = l;
 	}
@@ -308,7 +312,7 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict
 		float v = x[i];
 		float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
 		hi[i] = h;
-		lo[i] = v - h;
+		lo[i] = tf32_lo(v, h);
 	}
 }
 
@@ -330,7 +334,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
 				if (SPLIT) {
 					float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
 					bt[(size_t)(n0 + r) * k + k0 + tx] = h;
-					bt_lo[(size_t)(n0 + r) * k + k0 + tx] = v - h;
+					bt_lo[(size_t)(n0 + r) * k + k0 + tx] = tf32_lo(v, h);
 				} else {
 					bt[(size_t)(n0 + r) * k + k0 + tx] = v;
 				}

@@ -162,6 +162,24 @@ __global__ void __launch_bounds__(256) matmul_tn_reduce_kernel(const float* __re
 }
 
 #ifndef TF_HOST_SIM
+// out[M, R] = in[R, M]^T through a 32x33 shared tile; grid.y strides over the rows (used only by the large-output fallback)
+__global__ void __launch_bounds__(256) transpose_rm_kernel(const float* __restrict__ in, float* __restrict__ out, long long R, long long M) {
+	__shared__ float tile[32][33];
+	const long long m0 = (long long)blockIdx.x * 32;
+	for (long long r0 = (long long)blockIdx.y * 32; r0 < R; r0 += (long long)gridDim.y * 32) {
+		for (int j = threadIdx.y; j < 32; j += 8) {
+			const long long rr = r0 + j, mm = m0 + threadIdx.x;
+			tile[j][threadIdx.x] = (rr < R && mm < M) ? in[rr * M + mm] : 0.f;
+		}
+		__syncthreads();
+		for (int j = threadIdx.y; j < 32; j += 8) {
+			const long long mm = m0 + j, rr = r0 + threadIdx.x;
+			if (mm < M && rr < R) out[mm * R + rr] = tile[threadIdx.x][j];
+		}
+		__syncthreads();
+	}
+}
+
 template <int BM, int BN, int TM, int TN>
 int launch_tn(const float* a, const float* b, float* c, size_t r, size_t m, size_t n) {
 	tfcuda::State& s = tfcuda::state();
@@ -201,8 +219,24 @@ extern "C" int tfcuda_matmul_tn(uint64_t a, uint64_t b, uint64_t c, size_t r, si
 	if (!s.initialized) { tfcuda::set_error("tfcuda_matmul_tn: not initialised"); return 1; }
 	if (m == 0 || n == 0) return 0;
 	if (r == 0) return tfcuda_memset32(c, 0, m * n);
-	if (m > 0x7fff || n > 0x7fff || m * n > 0x3fffffff) { tfcuda::set_error("tfcuda_matmul_tn: output extent out of range"); return 1; }
 	const float* pa = reinterpret_cast<const float*>(a);
+	if (m > 0x7fff || n > 0x7fff || m * n > 0x3fffffff) {
+		// A weight matrix this large (vocabulary / embedding sized layers) is not the split-K case the kernel below is built for - its
+		// partial products alone would be splits x M x N floats.  Materialise A^T once and hand the product to the dense matmul
+		// (fp32-accurate 3xTF32 mode, or FFMA where TMA cannot describe the operands): same contract, any extent.
+		if (r > 0x7fffffffull || m > 0x7fffffffull) { tfcuda::set_error("tfcuda_matmul_tn: extent exceeds 2^31-1"); return 1; }
+		float* at = nullptr;
+		TFCUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&at), r * m * sizeof(float), s.stream));
+		dim3 grid((unsigned)((m + 31) / 32), (unsigned)std::min<size_t>((r + 31) / 32, 65535));
+		{
+			tfcuda::ProfileScope prof("lib/matmul_tn_transpose", 8.0 * (double)r * (double)m);
+			transpose_rm_kernel<<<grid, dim3(32, 8), 0, s.stream>>>(pa, at, (long long)r, (long long)m);
+			if (tfcuda::check_launch("transpose_rm_kernel")) { cudaFreeAsync(at, s.stream); return 1; }
+		}
+		int rc = tfcuda_matmul(reinterpret_cast<uint64_t>(at), b, c, 1, m, n, r, 1);
+		cudaFreeAsync(at, tfcuda::state().stream);
+		return rc;
+	}
 	const float* pb = reinterpret_cast<const float*>(b);
 	float* pc = reinterpret_cast<float*>(c);
 	// narrow outputs (e.g. the 12 output channels of NCA's second layer) take a tall tile so that lanes are not wasted on padding

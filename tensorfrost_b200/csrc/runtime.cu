@@ -22,6 +22,7 @@
 #include <fstream>
 #include <sstream>
 #include <thread>
+#include <type_traits>
 #include <unordered_map>
 #include <vector>
 
@@ -34,7 +35,20 @@ static thread_local std::string g_error;
 static std::string g_error_shared;
 static std::mutex g_error_mutex;
 
-State& state() { return g_state; }
+static void flush_recorded();
+
+// Library kernels (reduce.cu, matmul*.cu, ...) begin with state(): launches recorded for graph replay (below) are issued first, so
+// everything that touches the stream directly stays in program order behind them.
+State& state() {
+	flush_recorded();
+	return g_state;
+}
+
+// the runtime stream for work issued directly (copies, memsets, allocations, events): recorded launches go first
+static cudaStream_t S() {
+	flush_recorded();
+	return S();
+}
 
 void set_error(const std::string& msg) {
 	g_error = msg;
@@ -88,22 +102,22 @@ static void flush_block_cache();
 
 void* scratch(size_t bytes) {
 	if (bytes <= g_scratch_bytes) return g_scratch;
-	if (g_scratch) cudaFreeAsync(g_scratch, g_state.stream);
+	if (g_scratch) cudaFreeAsync(g_scratch, S());
 	g_scratch = nullptr;
 	g_scratch_bytes = 0;
 	size_t want = (bytes + (bytes >> 3) + 0xfffff) & ~size_t(0xfffff);
 	void* p = nullptr;
-	cudaError_t e = cudaMallocAsync(&p, want, g_state.stream);
+	cudaError_t e = cudaMallocAsync(&p, want, S());
 	if (e != cudaSuccess) {
 		// parked tensor blocks / the driver pool may hold what the scratch needs: release them and ask for the exact size
 		(void)cudaGetLastError();
 		flush_block_cache();
-		cudaStreamSynchronize(g_state.stream);
+		cudaStreamSynchronize(S());
 		cudaMemPool_t mp;
 		if (cudaDeviceGetDefaultMemPool(&mp, g_state.device) == cudaSuccess) cudaMemPoolTrimTo(mp, 0);
 		(void)cudaGetLastError();
 		want = bytes;
-		e = cudaMallocAsync(&p, want, g_state.stream);
+		e = cudaMallocAsync(&p, want, S());
 	}
 	if (e != cudaSuccess) {
 		set_error("tfcuda: scratch allocation of " + std::to_string(bytes) + " bytes failed: " + cuda_err(e));
@@ -132,7 +146,7 @@ static BlockCache g_blocks;
 static void flush_block_cache() {
 	for (auto& kv : g_blocks.blocks)
 		for (void* p : kv.second) {
-			cudaFreeAsync(p, g_state.stream);
+			cudaFreeAsync(p, S());
 			g_blocks.driver_calls++;
 		}
 	g_blocks.blocks.clear();
@@ -154,18 +168,18 @@ static Buffer* create_buffer(size_t words) {
 		g_blocks.hits++;
 		// the previous tenant may have been up to 63 words longer (same 256-byte class): re-zero the slack behind this tensor
 		if (payload != words * sizeof(uint32_t))
-			cudaMemsetAsync(static_cast<char*>(p) + guard + words * sizeof(uint32_t), 0, payload - words * sizeof(uint32_t), g_state.stream);
+			cudaMemsetAsync(static_cast<char*>(p) + guard + words * sizeof(uint32_t), 0, payload - words * sizeof(uint32_t), S());
 	} else {
-		cudaError_t e = cudaMallocAsync(&p, total, g_state.stream);
+		cudaError_t e = cudaMallocAsync(&p, total, S());
 		g_blocks.driver_calls++;
 		if (e != cudaSuccess) {
 			// parked blocks / the driver pool may be holding memory another size could use: release and retry once
 			flush_block_cache();
-			cudaStreamSynchronize(g_state.stream);
+			cudaStreamSynchronize(S());
 			cudaMemPool_t mp;
 			if (cudaDeviceGetDefaultMemPool(&mp, g_state.device) == cudaSuccess) cudaMemPoolTrimTo(mp, 0);
 			(void)cudaGetLastError();
-			e = cudaMallocAsync(&p, total, g_state.stream);
+			e = cudaMallocAsync(&p, total, S());
 			g_blocks.driver_calls++;
 		}
 		if (e != cudaSuccess) {
@@ -174,8 +188,8 @@ static Buffer* create_buffer(size_t words) {
 			throw std::runtime_error(m);
 		}
 		if (guard) {
-			cudaMemsetAsync(p, 0, guard, g_state.stream);
-			cudaMemsetAsync(static_cast<char*>(p) + guard + words * sizeof(uint32_t), 0, total - guard - words * sizeof(uint32_t), g_state.stream);
+			cudaMemsetAsync(p, 0, guard, S());
+			cudaMemsetAsync(static_cast<char*>(p) + guard + words * sizeof(uint32_t), 0, total - guard - words * sizeof(uint32_t), S());
 		}
 	}
 	Buffer* b = new Buffer();
@@ -203,7 +217,7 @@ static void destroy_buffer(Buffer* b) {
 			g_blocks.blocks[total].push_back(p);
 			g_blocks.bytes += total;
 		} else {
-			cudaFreeAsync(p, g_state.stream);
+			cudaFreeAsync(p, S());
 			g_blocks.driver_calls++;
 		}
 	}
@@ -256,8 +270,8 @@ static uint32_t rt_readback(TFTensor t, size_t index, void*) {
 	require_init();
 	if (!t.buffer || index >= t.buffer->size) throw std::out_of_range("tfcuda: tf.read index out of range");
 	TFCUDA_THROW(cudaMemcpyAsync(g_state.pinned_word, reinterpret_cast<const void*>(dptr_of(t.buffer) + index * 4), 4,
-	                             cudaMemcpyDeviceToHost, g_state.stream));
-	TFCUDA_THROW(cudaStreamSynchronize(g_state.stream));
+	                             cudaMemcpyDeviceToHost, S()));
+	TFCUDA_THROW(cudaStreamSynchronize(S()));
 	return *g_state.pinned_word;
 }
 
@@ -300,10 +314,33 @@ static uint64_t fnv1a(const std::string& s, uint64_t h = 1469598103934665603ull)
 	return h;
 }
 
-static std::string cache_dir() {
-	const char* env = getenv("TFCUDA_CACHE_DIR");
-	std::string dir = env ? env : ("/tmp/tfcuda_cache_" + std::to_string((long)getuid()));
+// On-disk compile cache (cubins here, host-program libraries in the backend glue).  Default location: $TFCUDA_CACHE_DIR, else
+// $XDG_CACHE_HOME/tfcuda, else ~/.cache/tfcuda - never a predictable path under /tmp.  The directory must belong to this user and be
+// closed to everyone else (another user could otherwise plant device code that cuModuleLoadData would run in this process);
+// when that cannot be established the cache is disabled.
+static std::string make_cache_dir() {
+	if (getenv("TFCUDA_NO_CACHE") != nullptr) return "";
+	std::string dir;
+	if (const char* env = getenv("TFCUDA_CACHE_DIR")) {
+		dir = env;
+	} else if (const char* xdg = getenv("XDG_CACHE_HOME")) {
+		if (*xdg) dir = std::string(xdg) + "/tfcuda";
+	}
+	if (dir.empty()) {
+		const char* home = getenv("HOME");
+		if (!home || !*home) return "";
+		std::string base = std::string(home) + "/.cache";
+		mkdir(base.c_str(), 0700);
+		dir = base + "/tfcuda";
+	}
 	mkdir(dir.c_str(), 0700);
+	struct stat st;
+	if (lstat(dir.c_str(), &st) != 0 || !S_ISDIR(st.st_mode) || st.st_uid != getuid() || (st.st_mode & 077) != 0) return "";
+	return dir;
+}
+
+static const std::string& cache_dir() {
+	static const std::string dir = make_cache_dir();
 	return dir;
 }
 
@@ -338,6 +375,13 @@ struct Chunk {
 	bool from_cache = false;
 };
 
+// Cached cubin file = { magic, key length, second hash of the key, payload }: a 64-bit FNV name alone would accept a colliding or
+// truncated file.
+struct CubinHeader {
+	uint64_t magic, key_size, key_hash2, payload_size;
+};
+static const uint64_t kCubinMagic = 0x3130554355434654ull;  // "TFCUCU01"
+
 static void compile_chunk(Chunk& c, const std::vector<std::string>& opts, bool use_cache) {
 	std::string key_src = c.source;
 	for (auto& o : opts) key_src += "\x01" + o;
@@ -346,11 +390,19 @@ static void compile_chunk(Chunk& c, const std::vector<std::string>& opts, bool u
 	key_src += "\x01nvrtc" + std::to_string(maj) + "." + std::to_string(min);
 	char name[64];
 	snprintf(name, sizeof(name), "%016llx.cubin", (unsigned long long)fnv1a(key_src));
+	use_cache = use_cache && !cache_dir().empty();
+	const uint64_t hash2 = fnv1a(key_src, 0x9e3779b97f4a7c15ull);
 	std::string path = use_cache ? cache_dir() + "/" + name : std::string();
-	if (use_cache && read_file(path, c.cubin)) {
-		c.ok = true;
-		c.from_cache = true;
-		return;
+	std::string file;
+	if (use_cache && read_file(path, file) && file.size() > sizeof(CubinHeader)) {
+		CubinHeader h;
+		memcpy(&h, file.data(), sizeof(h));
+		if (h.magic == kCubinMagic && h.key_size == key_src.size() && h.key_hash2 == hash2 && h.payload_size == file.size() - sizeof(h)) {
+			c.cubin = file.substr(sizeof(h));
+			c.ok = true;
+			c.from_cache = true;
+			return;
+		}
 	}
 	nvrtcProgram prog = nullptr;
 	nvrtcResult r = nvrtcCreateProgram(&prog, c.source.c_str(), "tf_kernels.cu", 0, nullptr, nullptr);
@@ -379,7 +431,10 @@ static void compile_chunk(Chunk& c, const std::vector<std::string>& opts, bool u
 	nvrtcDestroyProgram(&prog);
 	c.ok = size > 0;
 	if (!c.ok) c.log += "\nempty cubin";
-	if (c.ok && use_cache) write_file_atomic(path, c.cubin);
+	if (c.ok && use_cache) {
+		CubinHeader h{kCubinMagic, key_src.size(), hash2, c.cubin.size()};
+		write_file_atomic(path, std::string(reinterpret_cast<const char*>(&h), sizeof(h)) + c.cubin);
+	}
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -411,7 +466,7 @@ void profile_begin(const char* name) {
 	if (!g_profile_on) return;
 	ProfileEntry& pe = g_profile[name];
 	ProfileSample smp{take_event(), take_event()};
-	cudaEventRecord(smp.a, g_state.stream);
+	cudaEventRecord(smp.a, S());
 	pe.pending.push_back(smp);
 }
 
@@ -419,13 +474,13 @@ void profile_end(const char* name, double bytes) {
 	if (!g_profile_on) return;
 	ProfileEntry& pe = g_profile[name];
 	if (pe.pending.empty()) return;
-	cudaEventRecord(pe.pending.back().b, g_state.stream);
+	cudaEventRecord(pe.pending.back().b, S());
 	pe.launches++;
 	pe.bytes += bytes;
 }
 
 static void profile_resolve() {
-	cudaStreamSynchronize(g_state.stream);
+	cudaStreamSynchronize(S());
 	for (auto& kv : g_profile) {
 		for (ProfileSample& smp : kv.second.pending) {
 			float ms = 0;
@@ -457,9 +512,222 @@ static bool load_entry(const char* sym, T& fn) {
 	return true;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Launch recorder + graph replay ("whole-program CUDA graph").
+//
+// A compiled TensorFrost program is a HOST function that allocates, dispatches and frees in a fixed order
+// (Backend/Backend.cpp:137-185 calls it once per prog(...)); on the reference backends every tf.dispatch is one driver launch.
+// Many programs are chains of short kernels over L2-resident data (the 32 multigrid sweeps of the fluid step take 3.6 us each,
+// almost all of it launch latency).  Between tfcuda_graph_begin and tfcuda_graph_end (the backend glue brackets every program
+// execution) tfcuda_launch therefore only RECORDS {function, grid, block, argument block}.  The list is issued when the program
+// ends - or earlier, the moment anything else needs the stream (a tf.read, a copy, a library kernel, a driver allocation: every
+// such path goes through S() / state()) - as ONE cudaGraphLaunch of a linear kernel-node chain:
+//   * exact hit   (same kernels, same argument bytes as an earlier execution: the pool hands out the same addresses every
+//                  step, or alternates between two sets when outputs are fed back)     -> cuGraphLaunch, nothing else;
+//   * shape hit   (same kernels, other arguments)                                      -> a new executable graph while fewer than
+//                  kExecsPerShape exist for the shape, else the least recently used one is patched node by node
+//                  (cuGraphExecKernelNodeSetParams on the nodes whose bytes differ);
+//   * miss                                                                              -> build + instantiate.
+// The argument bytes are baked into the nodes, so a replay launches exactly what eager execution would have launched, in the
+// same order; results are bit-identical (tests/test_graph_replay_gpu.py).  Lists shorter than kMinGraphOps are launched eagerly.
+// ------------------------------------------------------------------------------------------------
+struct RecOp {
+	CUfunction fn;
+	unsigned grid;
+	unsigned block[3];
+	uint32_t arg_offset, arg_bytes;
+};
+struct GraphExec {
+	CUgraph graph = nullptr;
+	CUgraphExec exec = nullptr;
+	std::vector<CUgraphNode> nodes;
+	std::vector<unsigned char> args;
+	uint64_t args_hash = 0;
+	uint64_t last_used = 0;
+};
+struct GraphShape {
+	std::vector<RecOp> ops;  // arg_offset / arg_bytes included: equal shapes have equal layouts
+	std::vector<GraphExec> execs;
+};
+struct Recorder {
+	int depth = 0;            // tfcuda_graph_begin nesting
+	bool enabled = false;     // TFCUDA_GRAPH (default on) and the driver entry points resolved
+	bool flushing = false;
+	std::vector<RecOp> ops;
+	std::vector<unsigned char> args;
+	std::unordered_map<uint64_t, GraphShape> shapes;
+	uint64_t tick = 0;
+	uint64_t replays = 0, exact_hits = 0, patched = 0, instantiated = 0, eager = 0;
+	std::string error;        // first failure of a deferred launch; reported by the next tfcuda_launch / tfcuda_graph_end / tfcuda_sync
+};
+static Recorder g_rec;
+static const size_t kMinGraphOps = 4;
+static const size_t kExecsPerShape = 4;
+static const size_t kMaxShapes = 256;
+
+static uint64_t hash_bytes(const void* p, size_t n, uint64_t h = 1469598103934665603ull) {
+	const unsigned char* b = static_cast<const unsigned char*>(p);
+	size_t i = 0;
+	for (; i + 8 <= n; i += 8) {
+		uint64_t w;
+		memcpy(&w, b + i, 8);
+		h = (h ^ w) * 1099511628211ull;
+		h ^= h >> 29;
+	}
+	for (; i < n; i++) h = (h ^ b[i]) * 1099511628211ull;
+	return h;
+}
+
+static bool rec_fail(const std::string& what, CUresult r) {
+	if (g_rec.error.empty()) g_rec.error = what + ": " + drv_err(r);
+	return false;
+}
+
+static bool launch_eager(const RecOp& op, const unsigned char* args) {
+	void* params[1] = {const_cast<unsigned char*>(args) + op.arg_offset};
+	CUresult r = g_state.drv.LaunchKernel(op.fn, op.grid, 1, 1, op.block[0], op.block[1], op.block[2], 0, (CUstream)g_state.stream, params, nullptr);
+	if (r != CUDA_SUCCESS) return rec_fail("cuLaunchKernel (deferred)", r);
+	return true;
+}
+
+static void fill_node_params(CUDA_KERNEL_NODE_PARAMS& kp, const RecOp& op, void** params) {
+	memset(&kp, 0, sizeof(kp));
+	kp.func = op.fn;
+	kp.gridDimX = op.grid; kp.gridDimY = 1; kp.gridDimZ = 1;
+	kp.blockDimX = op.block[0]; kp.blockDimY = op.block[1]; kp.blockDimZ = op.block[2];
+	kp.sharedMemBytes = 0;
+	kp.kernelParams = params;
+	kp.extra = nullptr;
+}
+
+static void destroy_exec(GraphExec& ge) {
+	if (ge.exec) g_state.drv.GraphExecDestroy(ge.exec);
+	if (ge.graph) g_state.drv.GraphDestroy(ge.graph);
+	ge = GraphExec();
+}
+
+static bool build_exec(GraphExec& ge, const std::vector<RecOp>& ops, const std::vector<unsigned char>& args) {
+	DriverApi& d = g_state.drv;
+	CUresult r = d.GraphCreate(&ge.graph, 0);
+	if (r != CUDA_SUCCESS) return rec_fail("cuGraphCreate", r);
+	ge.nodes.resize(ops.size());
+	for (size_t i = 0; i < ops.size(); i++) {
+		void* params[1] = {const_cast<unsigned char*>(args.data()) + ops[i].arg_offset};
+		CUDA_KERNEL_NODE_PARAMS kp;
+		fill_node_params(kp, ops[i], params);
+		r = d.GraphAddKernelNode(&ge.nodes[i], ge.graph, i ? &ge.nodes[i - 1] : nullptr, i ? 1 : 0, &kp);
+		if (r != CUDA_SUCCESS) {
+			destroy_exec(ge);
+			return rec_fail("cuGraphAddKernelNode", r);
+		}
+	}
+	r = d.GraphInstantiate(&ge.exec, ge.graph, 0);
+	if (r != CUDA_SUCCESS) {
+		destroy_exec(ge);
+		return rec_fail("cuGraphInstantiate", r);
+	}
+	ge.args = args;
+	return true;
+}
+
+static void flush_recorded() {
+	Recorder& R = g_rec;
+	if (R.ops.empty() || R.flushing) return;
+	R.flushing = true;
+	std::vector<RecOp> ops;
+	std::vector<unsigned char> args;
+	ops.swap(R.ops);
+	args.swap(R.args);
+	const size_t n = ops.size();
+	bool done = false;
+	if (n >= kMinGraphOps && R.error.empty()) {
+		const uint64_t shape_hash = hash_bytes(ops.data(), n * sizeof(RecOp));
+		const uint64_t args_hash = hash_bytes(args.data(), args.size());
+		if (R.shapes.size() >= kMaxShapes && !R.shapes.count(shape_hash)) {
+			for (auto& kv : R.shapes)
+				for (GraphExec& ge : kv.second.execs) destroy_exec(ge);
+			R.shapes.clear();
+		}
+		GraphShape& gs = R.shapes[shape_hash];
+		bool same_shape = gs.ops.size() == n && memcmp(gs.ops.data(), ops.data(), n * sizeof(RecOp)) == 0;
+		if (!same_shape) {  // first time, or a 64-bit collision: start over for this key
+			for (GraphExec& ge : gs.execs) destroy_exec(ge);
+			gs.execs.clear();
+			gs.ops = ops;
+		}
+		GraphExec* use = nullptr;
+		for (GraphExec& ge : gs.execs)
+			if (ge.args_hash == args_hash && ge.args.size() == args.size() && memcmp(ge.args.data(), args.data(), args.size()) == 0) {
+				use = &ge;
+				R.exact_hits++;
+				break;
+			}
+		if (!use && gs.execs.size() < kExecsPerShape) {
+			GraphExec ge;
+			if (build_exec(ge, ops, args)) {
+				ge.args_hash = args_hash;
+				gs.execs.push_back(std::move(ge));
+				use = &gs.execs.back();
+				R.instantiated++;
+			}
+		} else if (!use) {
+			GraphExec* lru = &gs.execs[0];
+			for (GraphExec& ge : gs.execs)
+				if (ge.last_used < lru->last_used) lru = &ge;
+			bool ok = true;
+			for (size_t i = 0; i < n && ok; i++) {
+				const RecOp& op = ops[i];
+				if (memcmp(lru->args.data() + op.arg_offset, args.data() + op.arg_offset, op.arg_bytes) == 0) continue;
+				void* params[1] = {args.data() + op.arg_offset};
+				CUDA_KERNEL_NODE_PARAMS kp;
+				fill_node_params(kp, op, params);
+				CUresult r = g_state.drv.GraphExecKernelNodeSetParams(lru->exec, lru->nodes[i], &kp);
+				if (r != CUDA_SUCCESS) ok = rec_fail("cuGraphExecKernelNodeSetParams", r);
+			}
+			if (ok) {
+				lru->args = args;
+				lru->args_hash = args_hash;
+				use = lru;
+				R.patched++;
+			}
+		}
+		if (use) {
+			CUresult r = g_state.drv.GraphLaunch(use->exec, (CUstream)g_state.stream);
+			if (r == CUDA_SUCCESS) {
+				use->last_used = ++R.tick;
+				R.replays++;
+				done = true;
+			} else {
+				rec_fail("cuGraphLaunch", r);
+			}
+		}
+	}
+	if (!done) {
+		for (size_t i = 0; i < n; i++)
+			if (!launch_eager(ops[i], args.data())) break;
+		R.eager += n;
+	}
+	g_state.launches += n;
+	R.flushing = false;
+}
+
+static void recorder_reset() {
+	for (auto& kv : g_rec.shapes)
+		for (GraphExec& ge : kv.second.execs) destroy_exec(ge);
+	g_rec = Recorder();
+}
+
 }  // namespace tfcuda
 
 using namespace tfcuda;
+
+// copy engines (tfcuda_memcpy_*_async below)
+static cudaStream_t g_up_stream = nullptr, g_down_stream = nullptr;
+static cudaEvent_t g_up_event = nullptr, g_down_event = nullptr, g_order_event = nullptr;
+static bool g_up_pending = false;
+static std::atomic<uint64_t> g_down_issued{0}, g_down_done{0};
+static void CUDART_CB download_done_cb(void*) { g_down_done.fetch_add(1, std::memory_order_release); }
 
 // ================================================================================================
 // C-ABI
@@ -474,6 +742,8 @@ const char* tfcuda_last_error(void) {
 }
 
 const char* tfcuda_prelude(void) { return kPrelude; }
+
+const char* tfcuda_cache_dir(void) { return cache_dir().c_str(); }
 
 int tfcuda_is_initialized(void) { return g_state.initialized ? 1 : 0; }
 
@@ -525,6 +795,26 @@ int tfcuda_init(int device) {
 			d.LaunchKernelEx = reinterpret_cast<decltype(d.LaunchKernelEx)>(p);
 		(void)cudaGetLastError();
 	}
+	{
+		// graph replay of recorded launches: on unless TFCUDA_GRAPH=0; needs the driver's graph entry points
+		const char* g = getenv("TFCUDA_GRAPH");
+		bool want = !(g && atoi(g) == 0);
+		auto opt = [](const char* sym, auto& fn) {
+			void* p = nullptr;
+			cudaDriverEntryPointQueryResult q;
+			if (cudaGetDriverEntryPoint(sym, &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && p) {
+				fn = reinterpret_cast<std::remove_reference_t<decltype(fn)>>(p);
+				return true;
+			}
+			(void)cudaGetLastError();
+			return false;
+		};
+		bool have = opt("cuGraphCreate", d.GraphCreate) & opt("cuGraphAddKernelNode", d.GraphAddKernelNode) &
+		            opt("cuGraphInstantiateWithFlags", d.GraphInstantiate) & opt("cuGraphLaunch", d.GraphLaunch) &
+		            opt("cuGraphExecKernelNodeSetParams", d.GraphExecKernelNodeSetParams) & opt("cuGraphExecDestroy", d.GraphExecDestroy) &
+		            opt("cuGraphDestroy", d.GraphDestroy);
+		g_rec.enabled = want && have;
+	}
 	TFCUDA_CHECK(cudaStreamCreateWithFlags(&g_state.stream, cudaStreamNonBlocking));
 	TFCUDA_CHECK(cudaMallocHost(&g_state.pinned_word, 64));
 	TFCUDA_CHECK(cudaEventCreate(&g_state.ev_begin));
@@ -540,13 +830,14 @@ int tfcuda_init(int device) {
 
 int tfcuda_shutdown(void) {
 	if (!g_state.initialized) return 0;
-	cudaStreamSynchronize(g_state.stream);
+	cudaStreamSynchronize(S());
+	recorder_reset();
 	for (auto& kv : g_pool.free_lists)
 		for (Buffer* b : kv.second) destroy_buffer(b);
 	g_pool.free_lists.clear();
 	g_pool.unused_words = 0;
 	flush_block_cache();
-	if (g_scratch) cudaFreeAsync(g_scratch, g_state.stream);
+	if (g_scratch) cudaFreeAsync(g_scratch, S());
 	g_scratch = nullptr;
 	g_scratch_bytes = 0;
 	for (CUmodule m : g_modules) g_state.drv.ModuleUnload(m);
@@ -555,6 +846,15 @@ int tfcuda_shutdown(void) {
 	cudaEventDestroy(g_state.ev_begin);
 	cudaEventDestroy(g_state.ev_end);
 	cudaFreeHost(g_state.pinned_word);
+	if (g_up_stream) {
+		cudaStreamDestroy(g_up_stream);
+		cudaStreamDestroy(g_down_stream);
+		cudaEventDestroy(g_up_event);
+		cudaEventDestroy(g_down_event);
+		cudaEventDestroy(g_order_event);
+		g_up_stream = g_down_stream = nullptr;
+		g_up_pending = false;
+	}
 	cudaStreamDestroy(g_state.stream);
 	g_state = State();
 	return 0;
@@ -562,14 +862,48 @@ int tfcuda_shutdown(void) {
 
 int tfcuda_device_sm_count(void) { return g_state.sm_count; }
 const char* tfcuda_device_name(void) { return g_state.device_name.c_str(); }
-void* tfcuda_stream(void) { return g_state.stream; }
+void* tfcuda_stream(void) { return g_state.initialized ? S() : nullptr; }
 
 int tfcuda_sync(void) {
 	if (!g_state.initialized) {
 		set_error("tfcuda_sync: not initialised");
 		return 1;
 	}
-	TFCUDA_CHECK(cudaStreamSynchronize(g_state.stream));
+	TFCUDA_CHECK(cudaStreamSynchronize(S()));
+	if (!g_rec.error.empty()) {
+		set_error("deferred launch failed: " + g_rec.error);
+		g_rec.error.clear();
+		return 1;
+	}
+	return 0;
+}
+
+int tfcuda_graph_begin(void) {
+	if (!g_state.initialized) { set_error("tfcuda_graph_begin: not initialised"); return 1; }
+	g_rec.depth++;
+	return 0;
+}
+
+int tfcuda_graph_end(void) {
+	if (!g_state.initialized) { set_error("tfcuda_graph_end: not initialised"); return 1; }
+	if (g_rec.depth > 0) g_rec.depth--;
+	if (g_rec.depth == 0) flush_recorded();
+	if (!g_rec.error.empty()) {
+		set_error("deferred launch failed: " + g_rec.error);
+		g_rec.error.clear();
+		return 1;
+	}
+	return 0;
+}
+
+int tfcuda_graph_stats(TFCudaGraphStats* out) {
+	if (!out) return 1;
+	out->enabled = g_rec.enabled ? 1 : 0;
+	out->replays = g_rec.replays;
+	out->exact_hits = g_rec.exact_hits;
+	out->patched = g_rec.patched;
+	out->instantiated = g_rec.instantiated;
+	out->eager_launches = g_rec.eager;
 	return 0;
 }
 
@@ -618,31 +952,88 @@ int tfcuda_buffer_read(const TFBuffer* buffer, size_t word_offset, uint32_t* dst
 int tfcuda_memcpy_h2d(uint64_t dst, const void* src, size_t bytes) {
 	if (!g_state.initialized) { set_error("tfcuda: not initialised"); return 1; }
 	if (bytes == 0) return 0;
-	TFCUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<void*>(dst), src, bytes, cudaMemcpyHostToDevice, g_state.stream));
+	TFCUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<void*>(dst), src, bytes, cudaMemcpyHostToDevice, S()));
 	// pageable sources are consumed before the call returns; pinned ones are not, so order the host too
-	TFCUDA_CHECK(cudaStreamSynchronize(g_state.stream));
+	TFCUDA_CHECK(cudaStreamSynchronize(S()));
 	return 0;
 }
 
 int tfcuda_memcpy_d2h(void* dst, uint64_t src, size_t bytes) {
 	if (!g_state.initialized) { set_error("tfcuda: not initialised"); return 1; }
 	if (bytes == 0) return 0;
-	TFCUDA_CHECK(cudaMemcpyAsync(dst, reinterpret_cast<const void*>(src), bytes, cudaMemcpyDeviceToHost, g_state.stream));
-	TFCUDA_CHECK(cudaStreamSynchronize(g_state.stream));
+	TFCUDA_CHECK(cudaMemcpyAsync(dst, reinterpret_cast<const void*>(src), bytes, cudaMemcpyDeviceToHost, S()));
+	TFCUDA_CHECK(cudaStreamSynchronize(S()));
+	return 0;
+}
+
+// ---- copy engines: uploads and downloads on their own streams, overlapping each other and the kernels (PCIe is full duplex) ----
+
+static int copy_streams_init() {
+	if (g_up_stream) return 0;
+	TFCUDA_CHECK(cudaStreamCreateWithFlags(&g_up_stream, cudaStreamNonBlocking));
+	TFCUDA_CHECK(cudaStreamCreateWithFlags(&g_down_stream, cudaStreamNonBlocking));
+	TFCUDA_CHECK(cudaEventCreateWithFlags(&g_up_event, cudaEventDisableTiming));
+	TFCUDA_CHECK(cudaEventCreateWithFlags(&g_down_event, cudaEventDisableTiming));
+	TFCUDA_CHECK(cudaEventCreateWithFlags(&g_order_event, cudaEventDisableTiming));
+	return 0;
+}
+
+int tfcuda_memcpy_h2d_async(uint64_t dst, const void* src, size_t bytes) {
+	if (!g_state.initialized) { set_error("tfcuda: not initialised"); return 1; }
+	if (bytes == 0) return 0;
+	if (copy_streams_init()) return 1;
+	// the copy starts once everything queued on the runtime stream SO FAR has finished (the previous users of dst)
+	TFCUDA_CHECK(cudaEventRecord(g_order_event, S()));
+	TFCUDA_CHECK(cudaStreamWaitEvent(g_up_stream, g_order_event, 0));
+	TFCUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<void*>(dst), src, bytes, cudaMemcpyHostToDevice, g_up_stream));
+	TFCUDA_CHECK(cudaEventRecord(g_up_event, g_up_stream));
+	g_up_pending = true;
+	return 0;
+}
+
+int tfcuda_wait_uploads(void) {
+	if (!g_state.initialized) { set_error("tfcuda: not initialised"); return 1; }
+	if (!g_up_pending) return 0;
+	TFCUDA_CHECK(cudaStreamWaitEvent(S(), g_up_event, 0));
+	g_up_pending = false;
+	return 0;
+}
+
+int tfcuda_memcpy_d2h_async(void* dst, uint64_t src, size_t bytes) {
+	if (!g_state.initialized) { set_error("tfcuda: not initialised"); return 1; }
+	if (bytes == 0) return 0;
+	if (copy_streams_init()) return 1;
+	TFCUDA_CHECK(cudaEventRecord(g_order_event, S()));
+	TFCUDA_CHECK(cudaStreamWaitEvent(g_down_stream, g_order_event, 0));
+	TFCUDA_CHECK(cudaMemcpyAsync(dst, reinterpret_cast<const void*>(src), bytes, cudaMemcpyDeviceToHost, g_down_stream));
+	TFCUDA_CHECK(cudaEventRecord(g_down_event, g_down_stream));
+	g_down_issued.fetch_add(1);
+	TFCUDA_CHECK(cudaLaunchHostFunc(g_down_stream, download_done_cb, nullptr));
+	return 0;
+}
+
+uint64_t tfcuda_downloads_issued(void) { return g_down_issued.load(); }
+uint64_t tfcuda_downloads_done(void) { return g_down_done.load(std::memory_order_acquire); }
+
+int tfcuda_copy_sync(void) {
+	if (!g_state.initialized) { set_error("tfcuda: not initialised"); return 1; }
+	if (!g_up_stream) return 0;
+	TFCUDA_CHECK(cudaStreamSynchronize(g_up_stream));
+	TFCUDA_CHECK(cudaStreamSynchronize(g_down_stream));
 	return 0;
 }
 
 int tfcuda_memcpy_d2d(uint64_t dst, uint64_t src, size_t bytes) {
 	if (!g_state.initialized) { set_error("tfcuda: not initialised"); return 1; }
 	if (bytes == 0) return 0;
-	TFCUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<void*>(dst), reinterpret_cast<const void*>(src), bytes, cudaMemcpyDeviceToDevice, g_state.stream));
+	TFCUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<void*>(dst), reinterpret_cast<const void*>(src), bytes, cudaMemcpyDeviceToDevice, S()));
 	return 0;
 }
 
 uint64_t tfcuda_malloc(size_t bytes) {
 	if (!g_state.initialized) { set_error("tfcuda: not initialised"); return 0; }
 	void* p = nullptr;
-	cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 4, g_state.stream);
+	cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 4, S());
 	if (e != cudaSuccess) {
 		set_error("tfcuda_malloc(" + std::to_string(bytes) + "): " + cuda_err(e));
 		return 0;
@@ -652,7 +1043,7 @@ uint64_t tfcuda_malloc(size_t bytes) {
 
 int tfcuda_free(uint64_t ptr) {
 	if (!ptr) return 0;
-	TFCUDA_CHECK(cudaFreeAsync(reinterpret_cast<void*>(ptr), g_state.stream));
+	TFCUDA_CHECK(cudaFreeAsync(reinterpret_cast<void*>(ptr), S()));
 	return 0;
 }
 
@@ -687,7 +1078,7 @@ int tfcuda_compile_kernels(const TFCudaKernelSource* kernels, size_t count, cons
 	if (count == 0) return 0;
 
 	std::vector<std::string> opts = nvrtc_options(options);
-	bool use_cache = getenv("TFCUDA_NO_CACHE") == nullptr;
+	bool use_cache = !cache_dir().empty();
 
 	// chunk the emitted kernels; each chunk is one NVRTC translation unit = prelude + kernels
 	const size_t kPerChunk = 12;
@@ -791,9 +1182,32 @@ int tfcuda_launch(size_t kernel_id, const uint64_t* mem, size_t n_mem, const uin
 	// grid.x is limited to 2^31-1: larger dispatches are split with the _kernel_block_offset word
 	const size_t kMaxGrid = 0x7fffffffull;
 	size_t done = 0;
-	ProfileScope prof(e.entry.c_str());
 	static const bool pdl_env = getenv("TFCUDA_PDL") != nullptr && atoi(getenv("TFCUDA_PDL")) != 0;
 	const bool pdl = pdl_env && g_state.drv.LaunchKernelEx != nullptr;
+	if (g_rec.depth > 0 && g_rec.enabled && !g_profile_on && !pdl) {
+		// inside a program execution: record, the list is replayed as one graph (see "Launch recorder")
+		if (!g_rec.error.empty()) {
+			set_error("deferred launch failed: " + g_rec.error);
+			g_rec.error.clear();
+			return 1;
+		}
+		while (done < work_group_count) {
+			size_t now = std::min(kMaxGrid, work_group_count - done);
+			if (offset_word) *offset_word = vars[n_var - 1] + (uint32_t)done;
+			RecOp op;
+			memset(&op, 0, sizeof(op));
+			op.fn = e.fn;
+			op.grid = (unsigned)now;
+			for (int d = 0; d < 3; d++) op.block[d] = e.group[d];
+			op.arg_offset = (uint32_t)g_rec.args.size();
+			op.arg_bytes = (uint32_t)bytes;
+			g_rec.args.insert(g_rec.args.end(), block, block + ((bytes + 7) & ~size_t(7)));
+			g_rec.ops.push_back(op);
+			done += now;
+		}
+		return 0;
+	}
+	ProfileScope prof(e.entry.c_str());
 	while (done < work_group_count) {
 		size_t now = std::min(kMaxGrid, work_group_count - done);
 		if (offset_word) *offset_word = vars[n_var - 1] + (uint32_t)done;
@@ -902,13 +1316,13 @@ int tfcuda_host_free(void* p) {
 
 int tfcuda_timer_begin(void) {
 	if (!g_state.initialized) { set_error("tfcuda: not initialised"); return 1; }
-	TFCUDA_CHECK(cudaEventRecord(g_state.ev_begin, g_state.stream));
+	TFCUDA_CHECK(cudaEventRecord(g_state.ev_begin, S()));
 	return 0;
 }
 
 int tfcuda_timer_end(float* ms) {
 	if (!g_state.initialized) { set_error("tfcuda: not initialised"); return 1; }
-	TFCUDA_CHECK(cudaEventRecord(g_state.ev_end, g_state.stream));
+	TFCUDA_CHECK(cudaEventRecord(g_state.ev_end, S()));
 	TFCUDA_CHECK(cudaEventSynchronize(g_state.ev_end));
 	TFCUDA_CHECK(cudaEventElapsedTime(ms, g_state.ev_begin, g_state.ev_end));
 	return 0;
@@ -927,6 +1341,6 @@ extern "C" int tfcuda_memset32(uint64_t dst, uint32_t value, size_t words) {
 	if (!g_state.initialized) { set_error("tfcuda: not initialised"); return 1; }
 	if (words == 0) return 0;
 	size_t blocks = std::min<size_t>((words + 255) / 256, (size_t)g_state.sm_count * 8);
-	tfcuda_fill32_kernel<<<(unsigned)blocks, 256, 0, g_state.stream>>>(reinterpret_cast<uint32_t*>(dst), value, words);
+	tfcuda_fill32_kernel<<<(unsigned)blocks, 256, 0, S()>>>(reinterpret_cast<uint32_t*>(dst), value, words);
 	return check_launch("tfcuda_memset32");
 }

@@ -25,6 +25,15 @@ struct DriverApi {
 	CUresult (*LaunchKernelEx)(const CUlaunchConfig*, CUfunction, void**, void**) = nullptr;  // optional (TFCUDA_PDL)
 	CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
 	CUresult (*FuncGetAttribute)(int*, CUfunction_attribute, CUfunction) = nullptr;
+	// graph replay of recorded launches (runtime.cu "Launch recorder"); optional: without them launches stay eager
+	CUresult (*GraphCreate)(CUgraph*, unsigned) = nullptr;
+	CUresult (*GraphAddKernelNode)(CUgraphNode*, CUgraph, const CUgraphNode*, size_t, const CUDA_KERNEL_NODE_PARAMS*) = nullptr;
+	CUresult (*GraphInstantiate)(CUgraphExec*, CUgraph, unsigned long long) = nullptr;
+	CUresult (*GraphLaunch)(CUgraphExec, CUstream) = nullptr;
+	CUresult (*GraphExecKernelNodeSetParams)(CUgraphExec, CUgraphNode, const CUDA_KERNEL_NODE_PARAMS*) = nullptr;
+	CUresult (*GraphExecDestroy)(CUgraphExec) = nullptr;
+	CUresult (*GraphDestroy)(CUgraph) = nullptr;
+	CUresult (*GraphAddDependencies_v2)(CUgraph, const CUgraphNode*, const CUgraphNode*, const CUgraphEdgeData*, size_t) = nullptr;
 };
 
 struct State {

@@ -163,14 +163,14 @@ class NcaTrainer:
     """One rank of the data-parallel NCA trainer (world == 1: plain single-GPU training)."""
 
     def __init__(self, tf, global_batch=256, grid=128, pool_size=1024, train_steps=25, rank=0, world=1, seed=0, mono=False,
-                 channel_n=12, exchange=None, rank_seed_offset=1000003):
+                 channel_n=12, exchange=None, rank_seed_offset=1000003, quantize=True):
         """exchange(flat_tensor, world) -> flat_tensor: the gradient exchange; default = tf.cuda_allreduce (NCCL, in place).
         Tests on the CPU oracle backend inject a gloo exchange."""
         self.tf, self.rank, self.world, self.mono = tf, rank, world, mono
         self.exchange = exchange
         self.batch, self.pool_shard = shard_sizes(global_batch, pool_size, world)
         self.grid, self.train_steps = grid, train_steps
-        nca = workloads.load_nca(tf, self.batch, grid, pool_size=self.pool_shard, train_steps=train_steps, channel_n=channel_n)
+        nca = workloads.load_nca(tf, self.batch, grid, pool_size=self.pool_shard, train_steps=train_steps, channel_n=channel_n, quantize=quantize)
         self.nca = nca
         grad_step, apply_step, mono_step, self.grad_shapes = build_programs(tf, nca, train_steps)
         if mono:
@@ -229,14 +229,19 @@ class NcaTrainer:
         # (grad 75.1 + exchange 0.5 + apply 0.15), which is also what 8 independent single-GPU processes take.  The host sync is free
         # here (every step already starts with one: the batch ids are uploaded), so the exchange is bracketed by default;
         # self.diag ("async" / "before" / "after" / "skip") overrides it for diagnosis.
-        diag = getattr(self, "diag", "") or ("before+after" if self.exchange is None and os.environ.get("TFCUDA_DP_SYNC", "1") != "0" else "async")
+        # The peer-memory exchange (default) is one kernel of ours on the runtime stream: no NCCL launch path, nothing to drain.
+        method = getattr(self, "method", "nccl")
+        drain = self.exchange is None and method == "nccl" and os.environ.get("TFCUDA_DP_SYNC", "1") != "0"
+        diag = getattr(self, "diag", "") or ("before+after" if drain else "async")
         if self.world > 1 and "skip" not in diag:
             if "before" in diag:
                 tf.cuda_synchronize()
             if self.exchange is not None:
                 flat = self.exchange(flat, self.world)
+            elif method == "peer":
+                tf.cuda_allreduce(flat, 1.0 / self.world, "peer")
             else:
-                tf.cuda_allreduce(flat, 1.0 / self.world)
+                tf.cuda_allreduce(flat, 1.0 / self.world, "nccl")
             if "after" in diag:
                 tf.cuda_synchronize()
         if phases is not None:
@@ -261,69 +266,101 @@ class NcaTrainer:
 # communicator bootstrap: the NCCL unique id travels through torch.distributed's rendezvous store
 # ----------------------------------------------------------------------------------------------------------------------
 def init_comm(tf, rank, world):
+    """Sets up the gradient exchange: the NCCL communicator (always: fallback and large payloads) and, unless
+    TFCUDA_DP_EXCHANGE=nccl, the one-shot peer-memory exchange (csrc/comm.cu: every rank maps every peer's exchange buffer through
+    CUDA IPC handles, shared here over the control-plane process group).  Returns the exchange in use: "peer" | "nccl"."""
     if world == 1:
-        return None
+        return "none"
     import torch.distributed as dist
-    if rank == 0:
-        uid = tf.cuda_comm_unique_id()
-        box = [uid]
-    else:
-        box = [None]
+    box = [tf.cuda_comm_unique_id()] if rank == 0 else [None]
     dist.broadcast_object_list(box, src=0)
     tf.cuda_comm_init(box[0], rank, world)
-    return box[0]
+    if os.environ.get("TFCUDA_DP_EXCHANGE", "peer") == "nccl" or not hasattr(tf, "cuda_peer_export"):
+        return "nccl"
+    try:
+        handle = tf.cuda_peer_export()
+        handles = [None] * world
+        dist.all_gather_object(handles, handle)
+        tf.cuda_peer_init(handles, rank, world)
+        ok = 1
+    except RuntimeError as e:  # no peer access between these devices: every rank must take the same decision
+        sys.stderr.write(f"[nca_dp rank {rank}] peer-memory exchange unavailable ({e}); using NCCL\n")
+        ok = 0
+    votes = [None] * world
+    dist.all_gather_object(votes, ok)
+    dist.barrier()
+    return "peer" if all(votes) else "nccl"
+
+
+def _timed_iterations(tf, tr, steps, dist=None):
+    """K iterations bracketed by device syncs (and a barrier across ranks); returns (device ms by CUDA events, host ms spent enqueuing)."""
+    tf.cuda_synchronize()
+    if dist is not None:
+        dist.barrier()
+    tf.cuda_timer_begin()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.step()
+    host_ms = (time.perf_counter() - t0) * 1e3
+    ms = tf.cuda_timer_end()
+    tf.cuda_synchronize()
+    return ms, host_ms
 
 
 def bench_main(args):
-    """bench.py --workload nca: K training iterations, strong scaling (global batch fixed, split across ranks).
-    value = samples/s over all ranks."""
+    """bench.py --workload nca (the default under torchrun with N > 1): K training iterations of the data-parallel NCA config, strong
+    scaling (global batch fixed, split across ranks); value = samples/s over all ranks, time = CUDA events on every rank's stream,
+    max over ranks.  The line also carries what the scaling is measured against, taken in the same job on rank 0's GPU while the other
+    ranks wait: `weak.alone_ms_per_step` (the same per-rank program without peers) and `single_gpu` (the whole global batch on one GPU)."""
+    import faulthandler
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # a hung collective must not hold the GPUs until the lease ends: dump every thread's stack and exit
+    faulthandler.dump_traceback_later(int(os.environ.get("TFCUDA_BENCH_DEADLINE", "800")), exit=True)
     dist = None
     if world > 1:
+        import datetime
         import torch  # before TensorFrost (SURVEY.md §7.3 item 9)
         import torch.distributed as dist
         torch.cuda.set_device(local)
-        dist.init_process_group("gloo")  # control plane only: barrier, id broadcast, max-over-ranks
+        dist.init_process_group("gloo", timeout=datetime.timedelta(seconds=900))  # control plane only: barriers, handle exchange, max-over-ranks
     import tensorfrost_b200
     weak = bool(getattr(args, "nca_weak", False))
     if weak:
         # weak scaling (SURVEY.md 8d C5): the per-GPU batch and pool shard stay at --nca-batch / --nca-pool, the global ones grow with N
         args.nca_batch *= world
         args.nca_pool *= world
-    devnull = os.open(os.devnull, os.O_WRONLY)
-    saved = os.dup(1)
-    os.dup2(devnull, 1)
-    try:
+    sys.path.insert(0, REPO_ROOT)
+    from bench import ClockSampler, quiet_stdout  # nvidia-smi clocks / throttle reasons of THIS rank's GPU during the timed region
+    with quiet_stdout():
         tf = tensorfrost_b200.load()
-        init_comm(tf, rank, world)
+        method = init_comm(tf, rank, world)
         t0 = time.perf_counter()
         tr = NcaTrainer(tf, global_batch=args.nca_batch, grid=args.nca_grid, pool_size=args.nca_pool, train_steps=args.nca_steps,
                         rank=rank, world=world, mono=args.nca_mono)
+        tr.method = method
         build_s = time.perf_counter() - t0
         for _ in range(max(args.warmup, 3)):
             tr.step()
-        tf.cuda_synchronize()
-        if dist is not None:
-            dist.barrier()
-        sys.path.insert(0, REPO_ROOT)
-        from bench import ClockSampler  # nvidia-smi clocks / throttle reasons of THIS rank's GPU during the timed region
         sampler = ClockSampler(local)
         sampler.start()
         launches0 = tf.cuda_launch_count()
         driver_calls0 = tf.cuda_pool_driver_calls()
-        tf.cuda_timer_begin()
-        host_t0 = time.perf_counter()
-        for _ in range(args.steps):
-            tr.step()
-        host_issue_ms = (time.perf_counter() - host_t0) * 1e3  # host time to ENQUEUE the steps (it runs ahead of the device)
-        ms = tf.cuda_timer_end()
-        tf.cuda_synchronize()
+        ms, host_issue_ms = _timed_iterations(tf, tr, args.steps, dist)
         clocks = sampler.stop()
         launches = tf.cuda_launch_count() - launches0
         driver_calls = tf.cuda_pool_driver_calls() - driver_calls0
+        graph = tf.cuda_graph_stats() if hasattr(tf, "cuda_graph_stats") else None
         loss = tr.step(read_loss=True)
+        # replicated state must be bit-identical on every rank (the optimizer step is replicated, nothing is broadcast)
+        digest = None
+        if not args.nca_mono:
+            import hashlib
+            h = hashlib.sha256()
+            for p in tr.parameters_numpy():
+                h.update(np.ascontiguousarray(p).tobytes())
+            digest = h.hexdigest()
         phase_ms = None
         if os.environ.get("TFCUDA_NCA_PHASES"):
             # diagnosis: three more steps with a device sync after each phase (grad program / gradient exchange / apply program)
@@ -339,13 +376,8 @@ def bench_main(args):
             for mode in ("async", "before", "after", "before+after", "skip", "async"):
                 tr.diag = mode
                 tr.step()
-                tf.cuda_synchronize()
-                if dist is not None:
-                    dist.barrier()
-                tf.cuda_timer_begin()
-                for _ in range(3):
-                    tr.step()
-                diag_ms[mode + ("#2" if mode in diag_ms else "")] = tf.cuda_timer_end() / 3
+                d_ms, _ = _timed_iterations(tf, tr, 3, dist)
+                diag_ms[mode + ("#2" if mode in diag_ms else "")] = d_ms / 3
             tr.diag = ""
         top = None
         if getattr(args, "nca_profile", False):
@@ -354,48 +386,77 @@ def bench_main(args):
             tf.cuda_profile_enable(True)
             tr.step()
             tf.cuda_profile_enable(False)
-        if getattr(args, "nca_profile", False) and rank == 0:
-            recs = sorted(tf.cuda_profile_records(), key=lambda r: -r["total_ms"])
-            total = sum(r["total_ms"] for r in recs)
-            top = [{"name": r["name"], "launches": r["launches"], "ms": round(r["total_ms"], 3), "share": round(r["total_ms"] / total, 4),
-                    "gbs": round(r["bytes"] / max(r["total_ms"], 1e-9) / 1e6, 1)} for r in recs[:24]]
-            dump = os.environ.get("TFCUDA_PROFILE_DUMP")
-            if dump:
-                with open(dump, "w") as f:
-                    json.dump(recs, f)
-            top.append({"name": "TOTAL", "launches": sum(r["launches"] for r in recs), "ms": round(total, 3), "gb": round(sum(r["bytes"] for r in recs) / 1e9, 2)})
+            if rank == 0:
+                recs = sorted(tf.cuda_profile_records(), key=lambda r: -r["total_ms"])
+                total = sum(r["total_ms"] for r in recs)
+                top = [{"name": r["name"], "launches": r["launches"], "ms": round(r["total_ms"], 3), "share": round(r["total_ms"] / total, 4),
+                        "gbs": round(r["bytes"] / max(r["total_ms"], 1e-9) / 1e6, 1)} for r in recs[:24]]
+                dump = os.environ.get("TFCUDA_PROFILE_DUMP")
+                if dump:
+                    with open(dump, "w") as f:
+                        json.dump(recs, f)
+                top.append({"name": "TOTAL", "launches": sum(r["launches"] for r in recs), "ms": round(total, 3), "gb": round(sum(r["bytes"] for r in recs) / 1e9, 2)})
+        per_rank_ms, digests = [ms / args.steps], [digest]
+        alone = single = None
         if dist is not None:
-            import torch
-            every = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
-            dist.all_gather(every, torch.tensor([ms], dtype=torch.float64))
-            per_rank_ms = [float(t.item()) / args.steps for t in every]
-            ms = max(float(t.item()) for t in every)
-            dist.barrier()
-    finally:
-        os.dup2(saved, 1)
+            every = [None] * world
+            dist.all_gather_object(every, (ms, digest))
+            per_rank_ms = [e[0] / args.steps for e in every]
+            digests = [e[1] for e in every]
+            ms = max(e[0] for e in every)
+            if not getattr(args, "no_single", False):
+                # references for the scaling numbers, on rank 0's GPU while the peers idle at the barrier below:
+                if rank == 0:
+                    # (weak) the SAME per-rank program and batch without peers: T(1 GPU, B/N) against T(N GPUs, B/N each)
+                    tr.diag = "skip"
+                    for _ in range(2):
+                        tr.step()
+                    a_ms, _ = _timed_iterations(tf, tr, args.steps)
+                    tr.diag = ""
+                    alone = {"alone_ms_per_step": a_ms / args.steps, "per_gpu_batch": args.nca_batch // world,
+                             "note": "rank 0's per-rank program without the exchange while the other GPUs idle"}
+                    # (strong) the whole global batch on ONE GPU: T(1 GPU, B)
+                    t1 = time.perf_counter()
+                    one = NcaTrainer(tf, global_batch=args.nca_batch, grid=args.nca_grid, pool_size=args.nca_pool, train_steps=args.nca_steps,
+                                     rank=0, world=1)
+                    for _ in range(3):
+                        one.step()
+                    s_ms, _ = _timed_iterations(tf, one, max(3, args.steps // 2))
+                    s_ms /= max(3, args.steps // 2)
+                    single = {"ms_per_step": s_ms, "samples_per_s": args.nca_batch / (s_ms / 1e3), "global_batch": args.nca_batch,
+                              "build_seconds": time.perf_counter() - t1, "note": "the whole global batch on rank 0's GPU alone, same job, same box"}
+                    del one
+                dist.barrier()
     if rank == 0:
         samples = args.nca_batch * args.steps
         line = {
             "metric": "NCA training samples/s", "value": samples / (ms / 1e3), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"NCA training (examples/ML/NCA), global batch {args.nca_batch} of {args.nca_grid}x{args.nca_grid}x12, "
+            "config": {"workload": f"NCA training (examples/ML/NCA, BASELINE configs[4]), global batch {args.nca_batch} of {args.nca_grid}x{args.nca_grid}x12, "
                                    f"{args.nca_steps} CA steps, pool {args.nca_pool}", "parallelism": f"dp{world}",
-                       "per_rank_batch": args.nca_batch // world, "exchange": "ncclAllReduce(sum) of 7821 fp32 + scale, once per step",
+                       "per_rank_batch": args.nca_batch // world,
+                       "exchange": {"peer": "one-shot allreduce kernel over NVLink peer memory (7821 fp32, rank-order sum) on the runtime stream",
+                                    "nccl": "ncclAllReduce(sum) of 7821 fp32 + scale, stream drained around it", "none": "none (1 GPU)"}[method],
                        "program": "reference single program" if args.nca_mono else "grad program -> allreduce -> apply program"},
             "gpu_launches": int(launches), "loss_after": loss, "build_seconds": build_s, "clocks": clocks,
-            "host_issue_ms_per_step": host_issue_ms / args.steps, "device_alloc_calls_per_step": driver_calls / args.steps,
+            "host_issue_ms_per_step": host_issue_ms / args.steps, "device_alloc_calls_per_step": driver_calls / args.steps, "graph": graph,
+            "host_cores": os.cpu_count(),
+            "verify": {"ok": bool(np.isfinite(loss)) and len(set(digests)) == 1, "loss_finite": bool(np.isfinite(loss)),
+                       "parameters_bit_identical_across_ranks": len(set(digests)) == 1, "parity": "tests/test_nca_gpu.py (split and mono step vs reference golden)"},
         }
-        if world > 1:
-            line["per_rank_ms_per_step"] = per_rank_ms
-        line["host_cores"] = os.cpu_count()
         if phase_ms is not None:
             line["phase_ms_grad_exchange_apply"] = phase_ms
         if diag_ms is not None:
             line["diag_ms_per_step"] = diag_ms
         if top is not None:
             line["top_kernels"] = top
+        if world > 1:
+            line["per_rank_ms_per_step"] = per_rank_ms
+            line["weak"] = alone
+            line["single_gpu"] = single
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+    faulthandler.cancel_dump_traceback_later()
     return 0

@@ -27,6 +27,21 @@ void StartCUDA();
 void StopCUDA();
 void CudaFinish();
 void CudaRegion(const char* name, bool begin);
+// Brackets one execution of a compiled program (ExecuteProgram, Backend/Backend.cpp:137-185): between Begin and End the runtime
+// records the program's dispatches and replays them as one CUDA graph (tfcuda_graph_begin / tfcuda_graph_end).  No-op on other backends.
+void CudaProgramBegin();
+void CudaProgramEnd(bool may_throw);
+struct CudaProgramScope {
+	bool open = true;
+	CudaProgramScope() { CudaProgramBegin(); }
+	void Finish() { open = false; CudaProgramEnd(true); }
+	~CudaProgramScope() { if (open) CudaProgramEnd(false); }
+};
+
+// first statement of CompileKernelLibrary (Backends/CPU/KernelCompiler.cpp:93-113) in the overlay build: when it returns true the
+// compiled host program is already at `dll_name` (per-process file names + a content-addressed cache instead of the fixed
+// /tmp/generated_lib_<id>.cpp); false = not our backend, the reference path runs
+bool CudaHostProgramCache(const std::string& code, const char* dll_name, size_t program_id);
 
 // ---- library calls inside compiled programs (CudaLibrary.cpp) ---------------------------------------------------------
 // One hand-written libtfcuda kernel standing in for a lowered algorithmic op; `inputs` / `outputs` are binding indices into

@@ -1,8 +1,15 @@
 // Glue between the reference's backend interfaces and libtfcuda.so (see CUDA.h).
 // Errors are thrown as std::runtime_error, the reference's error contract (Backend/Backend.cpp:166-170).
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cstdio>
 #include <cstdlib>
+#include <fstream>
 
 #include "CUDA.h"
+#include "Backend/Backend.h"
+#include "Backend/Backends/CPU/KernelCompiler.h"
 
 #define TFCUDA_NO_ABI_STRUCTS  // TFBuffer/TFTensor/... come from Backend/TensorMemory.h here
 namespace tfcuda_abi {
@@ -31,6 +38,15 @@ void StopCUDA() { tfcuda_sync(); }
 
 void CudaFinish() {
 	if (tfcuda_sync() != 0) Fail("stream synchronisation failed");
+}
+
+void CudaProgramBegin() {
+	if (current_backend == BackendType::CUDA) tfcuda_graph_begin();
+}
+
+void CudaProgramEnd(bool may_throw) {
+	if (current_backend != BackendType::CUDA) return;
+	if (tfcuda_graph_end() != 0 && may_throw) Fail("a kernel launch of the program failed");
 }
 
 void CudaRegion(const char* name, bool begin) {
@@ -62,6 +78,69 @@ void TFCudaBuffer::SetDataAtOffset(size_t offset, const vector<uint32_t>& data) 
 void TFCudaBuffer::GetDataAtOffset(size_t offset, size_t count, uint32_t* data) {
 	if (offset + count > size) throw std::runtime_error("CUDA backend: readback exceeds buffer " + std::string(name ? name : "?"));
 	if (tfcuda_memcpy_d2h(data, device_ptr + offset * 4, count * 4) != 0) Fail("device to host copy failed");
+}
+
+// ---- host program: compile once, cache by content, never share a file name between processes -------------------------
+// The reference writes every program's host code to the FIXED path /tmp/generated_lib_<program id>.cpp and compiles it with a
+// g++ subprocess on every tf.compile (Backends/CPU/KernelCompiler.cpp:93-113).  Two ranks of a multi-GPU job tracing the same
+// program therefore overwrite each other's source while g++ reads it, and every process pays 0.5-7 s per program again.
+// Here the library is keyed by the hash of the generated text + compiler flags: a hit costs a symlink; a miss compiles from
+// <hash>.<pid>.<id>.cpp to <hash>.<pid>.<id>.so and renames it into place, so concurrent ranks never see a partial file.
+// `dll_name` is the unique path the reference chose with mktemp and dlopens next (KernelCompiler.cpp:135-153).
+// Active on the CUDA backend (and, for the CPU tests of this very function, on any backend when TFCUDA_HOST_CACHE=1).
+namespace {
+
+uint64_t Fnv1a(const std::string& s, uint64_t h) {
+	for (unsigned char c : s) {
+		h ^= c;
+		h *= 1099511628211ull;
+	}
+	return h;
+}
+
+}  // namespace
+
+bool CudaHostProgramCache(const std::string& code, const char* dll_name, size_t program_id) {
+	const char* force = getenv("TFCUDA_HOST_CACHE");
+	if (current_backend != BackendType::CUDA && !(force && atoi(force) != 0)) return false;
+	const std::string flags = kernelCompileOptions;
+	const std::string key = code + "\x01" + flags;
+	char name[80];
+	snprintf(name, sizeof(name), "host_%016llx%016llx", (unsigned long long)Fnv1a(key, 1469598103934665603ull),
+	         (unsigned long long)Fnv1a(key, 0x9e3779b97f4a7c15ull));
+	const std::string cache = tfcuda_cache_dir();
+	const bool cached = !cache.empty() && !(force && atoi(force) == 0);
+	const std::string final_so = cached ? cache + "/" + name + ".so" : std::string(dll_name);
+	struct stat st;
+	if (!(cached && stat(final_so.c_str(), &st) == 0 && st.st_size > 0)) {
+		const std::string unique = (cached ? cache + "/" + name : std::string(dll_name)) + "." + std::to_string((long)getpid()) + "." + std::to_string(program_id);
+		const std::string src = unique + ".cpp", tmp_so = unique + ".so";
+		{
+			std::ofstream out(src);
+			if (!out) throw std::runtime_error("CUDA backend: cannot write the generated host program to " + src);
+			out << code;
+		}
+		const std::string cmd = "g++ " + flags + " -w -shared -fPIC " + src + " -o " + tmp_so + " 2>&1";
+		std::string output;
+		FILE* pipe = popen(cmd.c_str(), "r");
+		if (!pipe) throw std::runtime_error("CUDA backend: popen(g++) failed");
+		char buffer[256];
+		while (fgets(buffer, sizeof(buffer), pipe) != nullptr) output += buffer;
+		int status = pclose(pipe);
+		if (!getenv("TFCUDA_KEEP_HOST_SOURCE")) unlink(src.c_str());
+		if (status != 0) {
+			unlink(tmp_so.c_str());
+			throw std::runtime_error("CUDA backend: host program compiler exited with status " + std::to_string(status) + "\nCompiler output:\n" + output);
+		}
+		if (rename(tmp_so.c_str(), final_so.c_str()) != 0) {
+			unlink(tmp_so.c_str());
+			throw std::runtime_error("CUDA backend: cannot move the compiled host program into " + final_so);
+		}
+	}
+	if (cached && symlink(final_so.c_str(), dll_name) != 0) {
+		throw std::runtime_error(std::string("CUDA backend: cannot link the cached host program to ") + dll_name);
+	}
+	return true;
 }
 
 void CudaKernelManager::CompileProgram(Program* program) {

@@ -13,6 +13,9 @@
 #include <Frontend/Python/PyTensor.h>
 #include <Frontend/Python/PyTensorMemory.h>
 
+#include <deque>
+#include <tuple>
+
 #include "CUDA.h"
 
 #define TFCUDA_NO_ABI_STRUCTS
@@ -130,6 +133,53 @@ void CudaDefinitions(py::module& m) {
 		Check(tfcuda_memcpy_d2h(info.ptr, DevPtr(t), (size_t)info.size * 4), "cuda_download");
 	}, "Copy a TensorMemory into an existing numpy array of the same size (a tf.cuda_pinned_array destination runs at full PCIe rate)");
 
+	// copy engines: uploads / downloads on their own streams (see include/tfcuda.h); arrays should come from tf.cuda_pinned_array
+	m.def("cuda_upload_async", [](PyTensorMemory& t, py::array arr) {
+		RequireCuda("cuda_upload_async");
+		py::buffer_info info = arr.request();
+		(void)FormatOf(info);
+		if (!(arr.flags() & py::array::c_style)) throw std::runtime_error("cuda_upload_async: the source array must be C-contiguous");
+		if ((size_t)info.size != GetSize(t.tensor_)) throw std::runtime_error("cuda_upload_async: element count mismatch");
+		Check(tfcuda_memcpy_h2d_async(DevPtr(t), info.ptr, (size_t)info.size * 4), "cuda_upload_async");
+	}, "Start copying a (page-locked) numpy array into a TensorMemory on the upload stream; kernels queued after tf.cuda_wait_uploads() see it");
+	m.def("cuda_wait_uploads", []() { Check(tfcuda_wait_uploads(), "cuda_wait_uploads"); },
+	      "Order the backend stream behind every upload started so far (no host wait)");
+	// a download in flight keeps its source tensor (and destination array) alive: references are parked here with the download's
+	// ticket and dropped once the copy engine reports it complete
+	static std::deque<std::tuple<uint64_t, py::object, py::object>> in_flight;
+	auto release_done = [](bool all) {
+		uint64_t done = all ? UINT64_MAX : tfcuda_downloads_done();
+		while (!in_flight.empty() && std::get<0>(in_flight.front()) <= done) in_flight.pop_front();
+	};
+	m.def("cuda_download_async", [release_done](py::object tensor, py::array arr) {
+		RequireCuda("cuda_download_async");
+		const PyTensorMemory& t = tensor.cast<const PyTensorMemory&>();
+		py::buffer_info info = arr.request(true);
+		(void)FormatOf(info);
+		if (!(arr.flags() & py::array::c_style)) throw std::runtime_error("cuda_download_async: the destination array must be C-contiguous");
+		if ((size_t)info.size != GetSize(t.tensor_)) throw std::runtime_error("cuda_download_async: element count mismatch");
+		Check(tfcuda_memcpy_d2h_async(info.ptr, DevPtr(t), (size_t)info.size * 4), "cuda_download_async");
+		in_flight.emplace_back(tfcuda_downloads_issued(), tensor, arr);
+		release_done(false);
+	}, "Start copying a TensorMemory into a (page-locked) numpy array on the download stream, after the work queued so far; "
+	   "read it after tf.cuda_copy_sync().  The tensor is kept alive until the copy has finished");
+	m.def("cuda_copy_sync", [release_done]() {
+		Check(tfcuda_copy_sync(), "cuda_copy_sync");
+		release_done(true);
+	}, "Wait for the upload and download streams");
+	m.def("cuda_graph_stats", []() {
+		TFCudaGraphStats st{};
+		tfcuda_graph_stats(&st);
+		py::dict d;
+		d["enabled"] = st.enabled != 0;
+		d["replays"] = st.replays;
+		d["exact_hits"] = st.exact_hits;
+		d["patched"] = st.patched;
+		d["instantiated"] = st.instantiated;
+		d["eager_launches"] = st.eager_launches;
+		return d;
+	}, "Counters of the launch recorder (graph replay of program dispatch chains)");
+
 	m.def("cuda_numpy", [](const PyTensorMemory& t) -> py::array {
 		RequireCuda("cuda_numpy");
 		std::vector<size_t> shape = t.Shape();
@@ -155,12 +205,36 @@ void CudaDefinitions(py::module& m) {
 		if (s.size() != 128) throw std::runtime_error("cuda_comm_init: unique id must be 128 bytes");
 		Check(tfcuda_comm_init(reinterpret_cast<const uint8_t*>(s.data()), rank, world), "cuda_comm_init");
 	});
-	m.def("cuda_allreduce", [](PyTensorMemory& t, float scale) {
+	m.def("cuda_peer_export", []() {
+		RequireCuda("cuda_peer_export");
+		uint8_t h[64];
+		Check(tfcuda_peer_export(h), "cuda_peer_export");
+		return py::bytes(reinterpret_cast<const char*>(h), 64);
+	}, "Allocate this rank's peer-memory exchange buffer and return its 64-byte CUDA IPC handle");
+	m.def("cuda_peer_init", [](std::vector<py::bytes> handles, int rank, int world) {
+		RequireCuda("cuda_peer_init");
+		if ((int)handles.size() != world) throw std::runtime_error("cuda_peer_init: one handle per rank expected");
+		std::string all;
+		for (auto& h : handles) {
+			std::string s = h;
+			if (s.size() != 64) throw std::runtime_error("cuda_peer_init: IPC handles are 64 bytes");
+			all += s;
+		}
+		Check(tfcuda_peer_init(reinterpret_cast<const uint8_t*>(all.data()), rank, world), "cuda_peer_init");
+	}, "Map every peer's exchange buffer (handles in rank order)");
+	m.def("cuda_peer_ready", []() { return tfcuda_peer_ready() != 0; });
+	m.def("cuda_allreduce", [](PyTensorMemory& t, float scale, const std::string& method) {
 		RequireCuda("cuda_allreduce");
 		if (t.GetFormat() != TFTypeFloat32) throw std::runtime_error("cuda_allreduce: float32 tensors only");
-		Check(tfcuda_comm_allreduce_sum_f32(DevPtr(t), GetSize(t.tensor_), scale), "cuda_allreduce");
-	}, py::arg("tensor"), py::arg("scale") = 1.0f, "In-place sum-allreduce over the NCCL communicator, then multiply by scale");
-	m.def("cuda_comm_destroy", []() { tfcuda_comm_destroy(); });
+		size_t count = GetSize(t.tensor_);
+		bool peer = method == "peer" || (method == "auto" && tfcuda_peer_ready() && count <= tfcuda_peer_max_count());
+		if (method != "peer" && method != "nccl" && method != "auto") throw std::runtime_error("cuda_allreduce: method must be auto, peer or nccl");
+		if (peer) Check(tfcuda_peer_allreduce_sum_f32(DevPtr(t), count, scale), "cuda_allreduce (peer memory)");
+		else Check(tfcuda_comm_allreduce_sum_f32(DevPtr(t), count, scale), "cuda_allreduce (NCCL)");
+	}, py::arg("tensor"), py::arg("scale") = 1.0f, py::arg("method") = "auto",
+	   "In-place sum-allreduce, then multiply by scale: one-shot kernel over NVLink peer memory for small tensors when the peer exchange "
+	   "is initialised (tf.cuda_peer_init), NCCL otherwise");
+	m.def("cuda_comm_destroy", []() { tfcuda_comm_destroy(); tfcuda_peer_destroy(); });
 
 	// ---- library call inside a traced program: tf.sort.radix on this backend (see overlay/python/install.py) ----------
 	m.def("cuda_library_active", []() {

@@ -88,8 +88,20 @@ def main():
                    "\t}\n")
     p.insert_after("\t\t\tcase BackendType::CPU:\n\t\t\t\t//already in the host program\n\t\t\t\tbreak;\n",
                    "\t\t\tcase BackendType::CUDA:\n\t\t\t\t//compiled above, all kernels of the program at once\n\t\t\t\tbreak;\n")
+    # every program execution is bracketed for the launch recorder (graph replay of the program's dispatch chain, include/tfcuda.h)
+    p.insert_before("\ttry {\n\t\tprogram->execute_callback(", "\tCudaProgramScope cuda_scope;\n")
+    p.insert_after("throw std::runtime_error(\"Error executing program \" + program->program_name + \": \" + e.what());\n\t}\n",
+                   "\tcuda_scope.Finish();\n")
     p.insert_before("\tif (current_backend == BackendType::OpenGL) {\n\t\tif (begin) {",
                     "\tif (current_backend == BackendType::CUDA) {\n\t\tCudaRegion(name, begin);\n\t}\n")
+    p.save()
+
+    # 3b. host program: per-process file names + content-addressed cache instead of the fixed /tmp/generated_lib_<id>.cpp
+    # (Backends/CPU/KernelCompiler.cpp:93-113); the reference path is untouched for every other backend
+    p = Patch(tf / "Backend" / "Backends" / "CPU" / "KernelCompiler.cpp")
+    p.insert_after('#include "KernelCompiler.h"\n', '#include "Backend/Backends/CUDA/CUDA.h"\n')
+    p.insert_after("char* dllName, size_t program_id) {\n",
+                   "\tif (CudaHostProgramCache(sourceCode, dllName, program_id)) return;\n")
     p.save()
 
     # 4. emitter dispatch (Backend/CodeGen/Generators.{h,cpp})

@@ -52,12 +52,12 @@ def fluid_parity_mouse(step, n, m):
     return np.array([m / 2 + 0.2 * m * np.cos(a), n / 2 + 0.2 * n * np.sin(a), 0.8 * np.cos(a + 1.0), 0.8 * np.sin(a + 1.0), 1.0], np.float32)
 
 
-def fluid_parity_run(tf, n, m, steps, vorticity=0.0):
+def fluid_parity_run(tf, n, m, steps, vorticity=0.0, program=None):
     """The parity scenario of the headline workload (tests/golden/make_golden_fluid.py on the oracle, tests/test_zz_fluid_gpu.py on the
     CUDA backend): `steps` steps from rest with the moving source, outputs fed back; returns [vx, vy, pressure, density, div, canvas] of the
     last step as numpy.  Notebook default parameters (vorticity confinement scale 0: with confinement on the program normalises the curl
     gradient, grad / (|grad| + 1e-5), which is discontinuous where the gradient vanishes and turns last-bit differences into O(1) ones)."""
-    fluid = load_fluid(tf, n, m)
+    fluid = program if program is not None else load_fluid(tf, n, m)
     state = fluid_inputs(n, m)
     state[5] = np.array([1.0, vorticity, 1.0, 1.0, 0.999, 0.999], np.float32)
     div = canvas = None
@@ -68,9 +68,11 @@ def fluid_parity_run(tf, n, m, steps, vorticity=0.0):
 
 
 # ---- C5: neural cellular automata training (examples/ML/NCA/nca.py) ---------------------------------------------------
-def load_nca(tf, batch_size, grid, pool_size=1024, train_steps=25, channel_n=12):
+def load_nca(tf, batch_size, grid, pool_size=1024, train_steps=25, channel_n=12, quantize=True):
     """Exec the NCA example as a module with its size constants overridden; returns the module namespace
-    (CAModel, CATrain, optimization_step, ...).  grid = TARGET_SIZE + 2*TARGET_PADDING."""
+    (CAModel, CATrain, optimization_step, ...).  grid = TARGET_SIZE + 2*TARGET_PADDING.
+    quantize=False replaces CAModel.quantize (round to 1/255 with a straight-through gradient, nca.py:58-59) by the identity: the
+    smooth variant the parity tests use to pin gradients at 1e-3 (with the rounding on, an ulp upstream flips cells)."""
     text, path = _source("nca_program.py.txt")
     mod = types.ModuleType("nca_workload")
     mod.__file__ = path
@@ -83,6 +85,8 @@ def load_nca(tf, batch_size, grid, pool_size=1024, train_steps=25, channel_n=12)
     mod.BATCH_SIZE = batch_size
     mod.POOL_SIZE = pool_size
     mod.DEFAULT_TRAIN_STEPS = train_steps
+    if not quantize:
+        mod.CAModel.quantize = lambda self, Xstate: Xstate
     return mod
 
 

@@ -22,7 +22,9 @@ class Case:
     build: Callable          # build(tf) -> compiled program (or a callable taking *tensors)
     make_inputs: Callable    # make_inputs(rng, size) -> list of numpy arrays
     kind: str = "float"      # "exact" | "float"
-    tol: float = 1e-5        # relative (to the output's max magnitude) for kind == "float"
+    tol: float = 1e-5        # element-wise relative bar for kind == "float": |got - ref| <= tol * max(|ref|, floor * max|ref|)
+    floor: float = 0.05      # absolute floor as a fraction of the output's max magnitude: elements below it are sums / differences
+                             # of O(max) terms (stencils, residuals, gradients), their error scales with the terms, not with them
     default_size: int = 64
     outputs: Optional[List[str]] = None
 
@@ -30,10 +32,10 @@ class Case:
 CASES = {}
 
 
-def case(name, kind="float", tol=1e-5, default_size=64, outputs=None):
+def case(name, kind="float", tol=1e-5, default_size=64, outputs=None, floor=0.05):
     def deco(fn):
         build, make_inputs = fn()
-        CASES[name] = Case(name, build, make_inputs, kind, tol, default_size, outputs)
+        CASES[name] = Case(name, build, make_inputs, kind, tol, floor, default_size, outputs)
         return fn
     return deco
 
@@ -624,5 +626,7 @@ def compare(c: Case, got, want):
             assert same_special, f"{c.name}[{k}]: NaN/Inf pattern differs"
             fin = np.isfinite(wf)
             scale = max(float(np.max(np.abs(wf[fin]))) if fin.any() else 0.0, 1e-30)
-            err = float(np.max(np.abs(gf[fin] - wf[fin]))) / scale if fin.any() else 0.0
-            assert err <= c.tol, f"{c.name}[{k}]: max error {err:.3e} relative to max|ref| exceeds {c.tol:.1e}"
+            floor = getattr(c, "floor", 0.05) * scale
+            err = float(np.max(np.abs(gf[fin] - wf[fin]) / np.maximum(np.abs(wf[fin]), floor))) if fin.any() else 0.0
+            assert err <= c.tol, (f"{c.name}[{k}]: element-wise error {err:.3e} (|got-ref| / max(|ref|, {getattr(c, 'floor', 0.05):g} max|ref|)) "
+                                  f"exceeds {c.tol:.1e}")

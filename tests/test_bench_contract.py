@@ -39,6 +39,11 @@ class _ScriptedDevice:
 
     def cuda_upload(self, t, a): self.uploads += 1
     def cuda_download(self, t, a): self.downloads += 1
+    def cuda_upload_async(self, t, a): self.uploads += 1
+    def cuda_download_async(self, t, a): self.downloads += 1
+    def cuda_wait_uploads(self): self.waits = getattr(self, "waits", 0) + 1
+    def cuda_copy_sync(self): self.copy_syncs = getattr(self, "copy_syncs", 0) + 1
+    def cuda_graph_stats(self): return {"enabled": True, "replays": 2, "exact_hits": 1, "patched": 0, "instantiated": 1, "eager_launches": 0}
 
 
 def test_cuda_arm_line_has_every_contract_key(monkeypatch):
@@ -46,7 +51,7 @@ def test_cuda_arm_line_has_every_contract_key(monkeypatch):
     from tensorfrost_b200 import workloads
     monkeypatch.setattr(workloads, "load_fluid", lambda tf, n, m: (lambda *s: [_T()] * 7))
     dev = _ScriptedDevice()
-    args = types.SimpleNamespace(size=2048, warmup=1, steps=2)
+    args = types.SimpleNamespace(size=2048, warmup=1, steps=2, no_verify=True)
     res = bench.bench_fluid(dev, None, 0, 1, args, bench.read_peaks())
     line = bench.make_line(args, 1, res)
     json.dumps(line)
@@ -62,7 +67,10 @@ def test_cuda_arm_line_has_every_contract_key(monkeypatch):
     assert roof["kernel"] == "kernel_0" and roof["traffic"] == pytest.approx(69036288.0)  # from the committed ncu capture
     e2e = line["e2e"]
     assert e2e["h2d_bytes_per_step"] == 4 * 2048 * 2048 * 4 == e2e["d2h_bytes_per_step"] and e2e["unit"] == "GB/s"
-    assert dev.uploads == 4 * args.steps and dev.downloads == 4 * args.steps + 1  # + the probe call before the timed region
+    # every step uploads its 4 input fields and downloads its 4 result fields inside the timed region (copy streams)
+    assert dev.uploads == 4 * args.steps and dev.downloads == 4 * args.steps and dev.waits == args.steps and dev.copy_syncs == 1
+    assert line["config"] == bench.fluid_config(2048)  # identical to the reference arm's (the driver compares the two arms' configs)
+    assert bench.fluid_step_bytes(2048) == 816840772  # = the live count of the runtime profiler on the B200 (BENCH_r01.json)
 
 
 def test_reference_arm_prints_one_json_line(tmp_path):
@@ -75,5 +83,7 @@ def test_reference_arm_prints_one_json_line(tmp_path):
     assert len(lines) == 1, lines
     line = json.loads(lines[0])
     assert line["impl"] == "reference" and line["metric"] == "fused-kernel HBM GB/s" and line["unit"] == "GB/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] == os.cpu_count()
+    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    import bench
+    assert line["config"] == bench.fluid_config(256)  # the same dict the CUDA arm prints (the driver compares the arms' configs)
     assert line["e2e"] == {"value": line["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

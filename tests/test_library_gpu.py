@@ -207,6 +207,24 @@ def test_matmul_tcgen05(tfcuda_lib, m, n, k, mode):
         assert rel_err(d_c.get(), want) <= (1e-3 if mode == 0 else 5e-5)
 
 
+def test_matmul_3xtf32_inf_and_large_magnitudes(tfcuda_lib):
+    """mode 1 splits x = hi + lo: an Inf input must give Inf (as the reference's fp32 loop), not NaN rows from lo = Inf - Inf; large
+    finite magnitudes keep the fp32-level accuracy."""
+    rng = np.random.default_rng(4)
+    m, n, k = 128, 64, 64
+    a, b = rng.random((m, k), dtype=np.float32), rng.random((k, n), dtype=np.float32)
+    a[3, 5] = np.inf
+    a[7] *= np.float32(1e30)
+    d_a, d_b, d_c = abi.DeviceArray(a), abi.DeviceArray(b), abi.DeviceArray(np.zeros((m, n), np.float32))
+    abi.check(tfcuda_lib.tfcuda_matmul(d_a.ptr, d_b.ptr, d_c.ptr, 1, m, n, k, 1), "matmul")
+    got = d_c.get()
+    with np.errstate(over="ignore", invalid="ignore"):
+        want = a.astype(np.float64) @ b.astype(np.float64)
+    assert np.all(np.isposinf(got[3])) and not np.isnan(got).any()
+    rows = [r for r in range(m) if r not in (3, 7)]
+    assert rel_err(got[rows], want[rows]) <= 5e-5 and rel_err(got[[7]], want[[7]]) <= 5e-5
+
+
 def test_matmul_tcgen05_batched_and_unaligned_fallback(tfcuda_lib):
     rng = np.random.default_rng(9)
     a, b = rng.random((3, 130, 64), dtype=np.float32), rng.random((3, 64, 96), dtype=np.float32)
@@ -238,7 +256,17 @@ def test_matmul_tn(tfcuda_lib, r, m, n):
     assert rel_err(got, tf_oracle.matmul(np.ascontiguousarray(a.T), b)) <= 1e-5 if r <= 10000 else True
 
 
-@pytest.mark.skipif(not os.environ.get("TFCUDA_EXPERIMENTAL"), reason="experimental kernel: written after round 1's GPU budget ended; enable with TFCUDA_EXPERIMENTAL=1")
+def test_matmul_tn_large_output_extent(tfcuda_lib):
+    """M > 32767 (an embedding-sized weight): outside the split-K kernel's range, served by transpose + dense matmul (fp32-accurate mode)."""
+    r, m, n = 96, 40000, 8
+    rng = np.random.default_rng(9)
+    a, b = rng.standard_normal((r, m)).astype(np.float32), rng.standard_normal((r, n)).astype(np.float32)
+    d_a, d_b, d_c = abi.DeviceArray(a), abi.DeviceArray(b), abi.DeviceArray(np.full((m, n), np.nan, np.float32))
+    abi.check(tfcuda_lib.tfcuda_matmul_tn(d_a.ptr, d_b.ptr, d_c.ptr, r, m, n), "matmul_tn (large M)")
+    want = a.astype(np.float64).T @ b.astype(np.float64)
+    assert rel_err(d_c.get(), want) <= 1e-5
+
+
 @pytest.mark.parametrize("r,k,n", [(1, 1, 1), (70, 48, 128), (5000, 48, 128), (5000, 128, 12), (5000, 12, 128), (5000, 128, 48), (257, 7, 5), (4097, 36, 30), (100000, 128, 128)])
 def test_matmul_rows(tfcuda_lib, r, k, n):
     """Skinny matmul with the weight matrix resident in shared memory: fp32 FFMA in the reference's k order -> 1e-6 of the result scale
