@@ -1169,14 +1169,15 @@ int tfcuda_launch(size_t kernel_id, const uint64_t* mem, size_t n_mem, const uin
 	}
 	if (work_group_count == 0) return 0;
 	// argument block = { uint* mem[n_mem]; uint var[n_var]; } passed by value as the single kernel parameter
-	alignas(8) unsigned char block[4096];
+	alignas(8) unsigned char block[4096 + 8];
 	size_t bytes = n_mem * 8 + n_var * 4;
-	if (bytes > sizeof(block)) {
+	if (bytes > 4096) {
 		set_error("tfcuda_launch: argument block too large");
 		return 1;
 	}
 	memcpy(block, mem, n_mem * 8);
 	memcpy(block + n_mem * 8, vars, n_var * 4);
+	memset(block + bytes, 0, 8);  // struct padding: recorded argument blocks are compared byte by byte
 	uint32_t* offset_word = n_var ? reinterpret_cast<uint32_t*>(block + n_mem * 8 + (n_var - 1) * 4) : nullptr;
 	void* params[1] = {block};
 	// grid.x is limited to 2^31-1: larger dispatches are split with the _kernel_block_offset word
@@ -1207,6 +1208,7 @@ int tfcuda_launch(size_t kernel_id, const uint64_t* mem, size_t n_mem, const uin
 		}
 		return 0;
 	}
+	flush_recorded();  // (nothing is pending unless the mode changed in the middle of a program)
 	ProfileScope prof(e.entry.c_str());
 	while (done < work_group_count) {
 		size_t now = std::min(kMaxGrid, work_group_count - done);
