@@ -570,20 +570,33 @@ def bench_extra(tf, peaks, quick):
                                 "roofline": {"bound": "fp32", "achieved": 20.0 * nb * nb / ms / 1e9, "peak": fp32_peak, "unit": "TFLOP/s",
                                              "frac": 20.0 * nb * nb / ms / 1e9 / fp32_peak, "note": "20 flop/interaction (SURVEY §8d C3); CUDA-core bound, not HBM"},
                                 "verify": {"ok": bool(err <= 1e-4), "max_rel_err_vs_float64_on_256_bodies": err}}
-        nbody = workloads.compile_nbody(tf)
-        ms = time_call(tf, lambda: nbody(x, v), 2, warm=1)
-        xn, vn = nbody(x, v)
-        err = check(tf.cuda_numpy(xn), tf.cuda_numpy(vn))
-        t0 = time.perf_counter()
-        xn, vn = nbody(tf.cuda_tensor(hx), v)
-        _ = tf.cuda_numpy(xn), tf.cuda_numpy(vn)
-        s = time.perf_counter() - t0
-        out["nbody_program"] = {"bodies": nb, "ms": ms, "ginteractions_per_s": nb * nb / ms / 1e6,
-                                "roofline": {"bound": "fp32", "achieved": 20.0 * nb * nb / ms / 1e9, "peak": fp32_peak, "unit": "TFLOP/s",
-                                             "frac": 20.0 * nb * nb / ms / 1e9 / fp32_peak},
-                                "note": "the reference's n_body program (n-body-benchmark.py:16-34) compiled by tf.compile on the CUDA backend",
-                                "verify": {"ok": bool(err <= 1e-4), "max_rel_err_vs_float64_on_256_bodies": err},
-                                "e2e": {"value": nb * nb / s / 1e9, "unit": "Ginteractions/s", "h2d_bytes_per_step": 12 * nb, "d2h_bytes_per_step": 24 * nb}}
+        for key, compile_fn, what in (("nbody_program", workloads.compile_nbody, "n_body (n-body-benchmark.py:16-34: broadcast differences + tf.sum)"),
+                                      ("nbody_loop_program", workloads.compile_nbody_loop, "n_body_loop (n-body-benchmark.py:36-65: one thread per body, tf.loop over partners)")):
+            nbody = compile_fn(tf)
+            ms = time_call(tf, lambda: nbody(x, v), 2, warm=1)
+            xn, vn = nbody(x, v)
+            # n_body_loop's force law differs from n_body's (the example divides by (d2 + eps) * dist and multiplies by dx twice): check it
+            # against its own float64 restatement
+            if key == "nbody_program":
+                err = check(tf.cuda_numpy(xn), tf.cuda_numpy(vn))
+            else:
+                idx = rng.choice(nb, 256, replace=False)
+                X = hx.astype(np.float64)
+                d = X[None, :, :] - X[idx, None, :]
+                d2 = (d ** 2).sum(-1)
+                g = -d[..., 0] / (d2 + 1e-4) / np.sqrt(d2 + 1e-4)
+                v_ref = (g[..., None] * d).sum(1) * 0.001
+                err = rel_err(tf.cuda_numpy(vn)[idx], v_ref, 1e-3 * float(np.max(np.abs(v_ref))))
+            t0 = time.perf_counter()
+            xn, vn = nbody(tf.cuda_tensor(hx), v)
+            _ = tf.cuda_numpy(xn), tf.cuda_numpy(vn)
+            s = time.perf_counter() - t0
+            out[key] = {"bodies": nb, "ms": ms, "ginteractions_per_s": nb * nb / ms / 1e6,
+                        "roofline": {"bound": "fp32", "achieved": 20.0 * nb * nb / ms / 1e9, "peak": fp32_peak, "unit": "TFLOP/s",
+                                     "frac": 20.0 * nb * nb / ms / 1e9 / fp32_peak},
+                        "note": "the reference's " + what + " compiled by tf.compile on the CUDA backend (drop-in path)",
+                        "verify": {"ok": bool(err <= 1e-4), "max_rel_err_vs_float64_on_256_bodies": err},
+                        "e2e": {"value": nb * nb / s / 1e9, "unit": "Ginteractions/s", "h2d_bytes_per_step": 12 * nb, "d2h_bytes_per_step": 24 * nb}}
 
     m = 4096 if quick else 8192
     shared = {}

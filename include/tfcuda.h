@@ -100,6 +100,7 @@ int tfcuda_is_initialized(void);
 int tfcuda_shutdown(void);
 const char* tfcuda_last_error(void);
 int tfcuda_device_sm_count(void);
+int tfcuda_device_index(void);          /* CUDA ordinal the backend runs on (-1 before tfcuda_init) */
 const char* tfcuda_device_name(void);
 void* tfcuda_stream(void);              /* the CUstream every launch / copy is ordered on */
 int tfcuda_sync(void);                  /* cuStreamSynchronize on that stream */

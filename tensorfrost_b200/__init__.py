@@ -48,10 +48,14 @@ def import_module():
     return _tf
 
 
-def load(kernel_compile_options=""):
+def load(kernel_compile_options=None):
     """`import TensorFrost as tf; tf.initialize(tf.cuda, options)` with the right module; returns tf.
+    `kernel_compile_options`: extra NVRTC flags for emitted kernels (the reference's kernel_compile_options string), e.g.
+    "-DTF_WARP_AGG_ATOMICS=0" or "--prec-div=false --prec-sqrt=false"; default: $TFCUDA_KERNEL_OPTIONS.
 
     Raises RuntimeError when no CUDA device is present (the backend never falls back to the CPU)."""
+    if kernel_compile_options is None:
+        kernel_compile_options = os.environ.get("TFCUDA_KERNEL_OPTIONS", "")
     tf = import_module()
     if str(tf.current_backend()) != str(tf.cuda):
         tf.initialize(tf.cuda, kernel_compile_options)

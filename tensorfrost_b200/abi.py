@@ -53,6 +53,7 @@ EXPORTS = {
     "tfcuda_shutdown": (i32, []),
     "tfcuda_last_error": (C.c_char_p, []),
     "tfcuda_device_sm_count": (i32, []),
+    "tfcuda_device_index": (i32, []),
     "tfcuda_device_name": (C.c_char_p, []),
     "tfcuda_stream": (C.c_void_p, []),
     "tfcuda_sync": (i32, []),

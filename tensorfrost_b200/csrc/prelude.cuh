@@ -97,7 +97,9 @@ TF_DEV float tf_atan(float x) { return atanf(x); }
 TF_DEV float tf_sinh(float x) { return sinhf(x); }
 TF_DEV float tf_cosh(float x) { return coshf(x); }
 TF_DEV float tf_tanh(float x) { return tanhf(x); }
-TF_DEV float tf_pow(float a, float b) { return powf(a, b); }
+// x ** 2.0 is how user programs square (n-body, losses): when the exponent is the literal 2 the branch folds at compile time to one
+// multiply - the correctly rounded square, which is also what the oracle's libm returns - instead of a ~40-instruction powf
+TF_DEV float tf_pow(float a, float b) { return b == 2.0f ? a * a : powf(a, b); }
 TF_DEV float tf_atan2(float a, float b) { return atan2f(a, b); }
 TF_DEV float tf_fma(float a, float b, float c) { return fmaf(a, b, c); }
 // Ops the op table lists (Operations.cpp:150-173) but the C++ helper header never defines, so they do
@@ -114,16 +116,56 @@ TF_DEV uint tf_pcg(uint v) {
 	uint word = ((state >> ((state >> 28u) + 4u)) ^ state) * 277803737u;
 	return (word >> 22u) ^ word;
 }
-TF_DEV float tf_pcgf(uint v) { return (float)tf_pcg(v) / (float)0xffffffffu; }
+// __fdiv_rn: correctly rounded whatever division mode the kernels are compiled with - random streams (dropout-style masks, NCA's
+// fire rate) must be the reference's bit for bit
+TF_DEV float tf_pcgf(uint v) { return __fdiv_rn((float)tf_pcg(v), (float)0xffffffffu); }
 
 // ---- barrier: a real one (the oracle's is a no-op, CPP.cpp:259) -------------------------------
 TF_DEV void tf_group_barrier() { __syncthreads(); }
 
 // ---- atomics on word buffers (CPP.cpp:141-257).  `mem` is the uint buffer (global or shared),
 // reinterpret per element type.  Float add is the native red/atom.add.f32, not a CAS loop. --------
+//
+// Warp-aggregated add (tf.scatterAdd, the autodiff of `load`: Implementations.cpp:185-194; broadcast gradients): the lanes of a warp
+// that are about to add to the SAME word are found with match.any, combined in registers (lane order: deterministic inside the warp)
+// and the group's lowest lane issues ONE red.global.add.  A lane alone at its address goes straight to the atomic.  Build kernels
+// with -DTF_WARP_AGG_ATOMICS=0 for the plain form.
+#ifndef TF_WARP_AGG_ATOMICS
+#define TF_WARP_AGG_ATOMICS 1
+#endif
+#if TF_WARP_AGG_ATOMICS && !defined(TF_HOST_SIM)
+TF_DEV uint tf_lane_id() {
+	uint l;
+	asm("mov.u32 %0, %%laneid;" : "=r"(l));
+	return l;
+}
+TF_DEV void tf_atomic_add(uint* mem, int a, float v) {
+	const uint active = __activemask();
+	const uint peers = __match_any_sync(active, (unsigned long long)(mem + a));
+	const int members = __popc(peers);
+	if (members == 1) {
+		atomicAdd((float*)mem + a, v);
+		return;
+	}
+	float sum = 0.0f;
+	for (int k = 1; k <= members; k++) sum += __shfl_sync(peers, v, (int)__fns(peers, 0, k));
+	if (tf_lane_id() == (uint)(__ffs((int)peers) - 1)) atomicAdd((float*)mem + a, sum);
+}
+TF_DEV void tf_atomic_add(uint* mem, int a, uint v) {
+	const uint peers = __match_any_sync(__activemask(), (unsigned long long)(mem + a));
+	if (__popc(peers) > 1) v = __reduce_add_sync(peers, v);
+	if (tf_lane_id() == (uint)(__ffs((int)peers) - 1)) atomicAdd(mem + a, v);
+}
+TF_DEV void tf_atomic_add(uint* mem, int a, int v) {
+	const uint peers = __match_any_sync(__activemask(), (unsigned long long)(mem + a));
+	if (__popc(peers) > 1) v = __reduce_add_sync(peers, v);
+	if (tf_lane_id() == (uint)(__ffs((int)peers) - 1)) atomicAdd((int*)mem + a, v);
+}
+#else
 TF_DEV void tf_atomic_add(uint* mem, int a, uint v) { atomicAdd(mem + a, v); }
 TF_DEV void tf_atomic_add(uint* mem, int a, int v) { atomicAdd((int*)mem + a, v); }
 TF_DEV void tf_atomic_add(uint* mem, int a, float v) { atomicAdd((float*)mem + a, v); }
+#endif
 TF_DEV uint tf_atomic_add_prev(uint* mem, int a, uint v) { return atomicAdd(mem + a, v); }
 TF_DEV int tf_atomic_add_prev(uint* mem, int a, int v) { return atomicAdd((int*)mem + a, v); }
 TF_DEV float tf_atomic_add_prev(uint* mem, int a, float v) { return atomicAdd((float*)mem + a, v); }

@@ -553,6 +553,7 @@ struct GraphShape {
 struct Recorder {
 	int depth = 0;            // tfcuda_graph_begin nesting
 	bool enabled = false;     // TFCUDA_GRAPH (default on) and the driver entry points resolved
+	bool pdl = false;         // TFCUDA_PDL=1: kernel nodes are chained with PROGRAMMATIC edges (kernels start with griddepcontrol.wait)
 	bool flushing = false;
 	std::vector<RecOp> ops;
 	std::vector<unsigned char> args;
@@ -612,14 +613,33 @@ static bool build_exec(GraphExec& ge, const std::vector<RecOp>& ops, const std::
 	CUresult r = d.GraphCreate(&ge.graph, 0);
 	if (r != CUDA_SUCCESS) return rec_fail("cuGraphCreate", r);
 	ge.nodes.resize(ops.size());
+	const bool pdl = g_rec.pdl && d.GraphAddDependencies_v2 != nullptr;
 	for (size_t i = 0; i < ops.size(); i++) {
 		void* params[1] = {const_cast<unsigned char*>(args.data()) + ops[i].arg_offset};
 		CUDA_KERNEL_NODE_PARAMS kp;
 		fill_node_params(kp, ops[i], params);
-		r = d.GraphAddKernelNode(&ge.nodes[i], ge.graph, i ? &ge.nodes[i - 1] : nullptr, i ? 1 : 0, &kp);
+		r = d.GraphAddKernelNode(&ge.nodes[i], ge.graph, (i && !pdl) ? &ge.nodes[i - 1] : nullptr, (i && !pdl) ? 1 : 0, &kp);
 		if (r != CUDA_SUCCESS) {
 			destroy_exec(ge);
 			return rec_fail("cuGraphAddKernelNode", r);
+		}
+	}
+	if (pdl && ops.size() > 1) {
+		// programmatic edges: node i+1 may be launched once every CTA of node i has executed griddepcontrol.launch_dependents (the
+		// first statement of every emitted kernel under TFCUDA_PDL=1); its own griddepcontrol.wait holds it until node i has completed
+		// and flushed, so the order of memory effects is the chain's.  What overlaps is the launch latency and the drain of node i.
+		const size_t m = ops.size() - 1;
+		std::vector<CUgraphEdgeData> edges(m);
+		memset(edges.data(), 0, m * sizeof(CUgraphEdgeData));
+		for (size_t i = 0; i < m; i++) {
+			edges[i].from_port = CU_GRAPH_KERNEL_NODE_PORT_PROGRAMMATIC;
+			edges[i].to_port = 0;
+			edges[i].type = CU_GRAPH_DEPENDENCY_TYPE_PROGRAMMATIC;
+		}
+		r = d.GraphAddDependencies_v2(ge.graph, ge.nodes.data(), ge.nodes.data() + 1, edges.data(), m);
+		if (r != CUDA_SUCCESS) {
+			destroy_exec(ge);
+			return rec_fail("cuGraphAddDependencies (programmatic)", r);
 		}
 	}
 	r = d.GraphInstantiate(&ge.exec, ge.graph, 0);
@@ -814,6 +834,8 @@ int tfcuda_init(int device) {
 		            opt("cuGraphExecKernelNodeSetParams", d.GraphExecKernelNodeSetParams) & opt("cuGraphExecDestroy", d.GraphExecDestroy) &
 		            opt("cuGraphDestroy", d.GraphDestroy);
 		g_rec.enabled = want && have;
+		const char* pdl_env = getenv("TFCUDA_PDL");
+		g_rec.pdl = pdl_env != nullptr && atoi(pdl_env) != 0 && opt("cuGraphAddDependencies", d.GraphAddDependencies_v2);
 	}
 	TFCUDA_CHECK(cudaStreamCreateWithFlags(&g_state.stream, cudaStreamNonBlocking));
 	TFCUDA_CHECK(cudaMallocHost(&g_state.pinned_word, 64));
@@ -861,6 +883,7 @@ int tfcuda_shutdown(void) {
 }
 
 int tfcuda_device_sm_count(void) { return g_state.sm_count; }
+int tfcuda_device_index(void) { return g_state.device; }
 const char* tfcuda_device_name(void) { return g_state.device_name.c_str(); }
 void* tfcuda_stream(void) { return g_state.initialized ? S() : nullptr; }
 
@@ -1185,7 +1208,7 @@ int tfcuda_launch(size_t kernel_id, const uint64_t* mem, size_t n_mem, const uin
 	size_t done = 0;
 	static const bool pdl_env = getenv("TFCUDA_PDL") != nullptr && atoi(getenv("TFCUDA_PDL")) != 0;
 	const bool pdl = pdl_env && g_state.drv.LaunchKernelEx != nullptr;
-	if (g_rec.depth > 0 && g_rec.enabled && !g_profile_on && !pdl) {
+	if (g_rec.depth > 0 && g_rec.enabled && !g_profile_on && (!pdl || g_rec.pdl)) {
 		// inside a program execution: record, the list is replayed as one graph (see "Launch recorder")
 		if (!g_rec.error.empty()) {
 			set_error("deferred launch failed: " + g_rec.error);

@@ -22,6 +22,8 @@ using namespace std;
 
 // NVRTC flags for emitted kernels (the kernel_compile_options string of tf.initialize)
 extern std::string cudaKernelCompileOptions;
+// value of a --tf-<name>=<value> token in that string (backend options, stripped before NVRTC sees the rest)
+std::string CudaBackendOption(const std::string& name, const std::string& fallback);
 
 void StartCUDA();
 void StopCUDA();

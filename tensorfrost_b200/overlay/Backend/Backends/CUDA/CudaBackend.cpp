@@ -26,6 +26,32 @@ namespace TensorFrost {
 
 std::string cudaKernelCompileOptions;
 
+// Backend options travel in the kernel_compile_options string of tf.initialize (Frontend/Python/PybindModule.cpp:112-115) next to
+// the NVRTC flags, as tokens of the form --tf-<name>=<value>; e.g. tf.initialize(tf.cuda, "--tf-matmul=tf32").
+//   --tf-matmul=3xtf32 | tf32 | fp32    precision of `a @ b` in compiled programs (default 3xtf32: fp32-accurate; tf32: one tensor-core
+//                                       product, 1e-3 class, ~3x faster; fp32: FFMA kernel)
+std::string CudaBackendOption(const std::string& name, const std::string& fallback) {
+	const std::string key = "--tf-" + name + "=";
+	size_t at = cudaKernelCompileOptions.find(key);
+	if (at == std::string::npos) return fallback;
+	size_t end = cudaKernelCompileOptions.find_first_of(" \t", at);
+	return cudaKernelCompileOptions.substr(at + key.size(), end == std::string::npos ? std::string::npos : end - at - key.size());
+}
+
+static std::string NvrtcOptions() {
+	std::string out;
+	size_t i = 0;
+	const std::string& s = cudaKernelCompileOptions;
+	while (i < s.size()) {
+		size_t j = s.find_first_of(" \t", i);
+		if (j == std::string::npos) j = s.size();
+		std::string tok = s.substr(i, j - i);
+		if (!tok.empty() && tok.rfind("--tf-", 0) != 0) out += (out.empty() ? "" : " ") + tok;
+		i = j + 1;
+	}
+	return out;
+}
+
 static void Fail(const std::string& what) {
 	throw std::runtime_error("CUDA backend: " + what + ": " + tfcuda_last_error());
 }
@@ -159,7 +185,7 @@ void CudaKernelManager::CompileProgram(Program* program) {
 		s.library_op = FindCudaLibraryCall(kernel.kernel_id_) != nullptr ? 1 : 0;  // no source: dispatched by DispatchCudaLibraryCall
 		sources.push_back(s);
 	}
-	if (tfcuda_compile_kernels(sources.data(), sources.size(), cudaKernelCompileOptions.c_str()) != 0) {
+	if (tfcuda_compile_kernels(sources.data(), sources.size(), NvrtcOptions().c_str()) != 0) {
 		Fail("kernel compilation failed for program " + program->program_name);
 	}
 }

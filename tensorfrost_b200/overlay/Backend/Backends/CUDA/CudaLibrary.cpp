@@ -206,7 +206,14 @@ void LowerMatmul(Tensors& outputs, map<int, const Tensor*> inputs, const Tensor*
 			return;
 		}
 	}
-	int mode = EnvInt("TFCUDA_MATMUL_MODE", 1);  // 1 = 3xTF32 (fp32-accurate) by default; 0 = single TF32; 2 = FFMA
+	// precision of the product: tf.initialize(tf.cuda, "--tf-matmul=tf32|3xtf32|fp32"), or TFCUDA_MATMUL_MODE=0|1|2 in the environment;
+	// default 3xTF32 (fp32-accurate: north_star's 1e-5 class); tf32 is inside north_star's 1e-3 matmul bar and ~3x faster
+	int mode = EnvInt("TFCUDA_MATMUL_MODE", 1);
+	const std::string opt = CudaBackendOption("matmul", "");
+	if (opt == "tf32") mode = 0;
+	else if (opt == "3xtf32") mode = 1;
+	else if (opt == "fp32") mode = 2;
+	else if (!opt.empty()) throw std::runtime_error("CUDA backend: --tf-matmul must be tf32, 3xtf32 or fp32");
 	vector<Tensor*> bufs = EmitLibraryCall(string(kMarker) + "matmul:" + to_string(mode), {a, b}, {{out_shape, tensor->node_->format}});
 	Tensor* result = ElementView(bufs[0], out_shape);
 	result->SetDebugName("matmul");

@@ -31,6 +31,64 @@ using namespace tfcuda_abi;
 
 namespace TensorFrost {
 
+
+// ---- bulk paths behind the reference's own tf.tensor(np) / .numpy (overlay insertions in Frontend/Python/PyTensorMemory.{h,cpp}) ----
+// tf.tensor(array): a C-contiguous 4-byte array goes to the device with ONE copy instead of the per-element std::function walk of
+// PyTensorMemory.cpp:15-84 (seconds at 2^28 elements).  Anything else (strided views, 8-byte dtypes, bool) returns false and takes
+// the reference path unchanged.
+bool CudaBulkTensor(const py::buffer_info& info, TFTensor** out) {
+	if (current_backend != BackendType::CUDA || info.itemsize != 4 || info.size <= 0 || info.ndim < 1) return false;
+	TFDataFormat fmt;
+	switch (info.format[0]) {
+		case 'f': fmt = TFTypeFloat32; break;
+		case 'i': case 'l': fmt = TFTypeInt32; break;
+		case 'I': case 'L': fmt = TFTypeUint32; break;
+		default: return false;
+	}
+	py::ssize_t expect = 4;
+	for (py::ssize_t d = info.ndim - 1; d >= 0; d--) {
+		if (info.shape[d] != 1 && info.strides[d] != expect) return false;
+		expect *= info.shape[d];
+	}
+	std::vector<size_t> shape(info.shape.begin(), info.shape.end());
+	TFTensor* t = global_memory_manager->AllocateTensor(shape, fmt);
+	if (tfcuda_memcpy_h2d(((TFCudaBuffer*)t->buffer)->GetNative(), info.ptr, (size_t)info.size * 4) != 0)
+		throw std::runtime_error(std::string("tf.tensor: upload failed: ") + tfcuda_last_error());
+	*out = t;
+	return true;
+}
+
+// .numpy: device -> the numpy array's own storage, no intermediate std::vector (PyTensorMemory.h:30-45)
+bool CudaBulkReadback(const TFTensor* t, void* dst, size_t item_size) {
+	if (current_backend != BackendType::CUDA || item_size != 4) return false;
+	size_t n = GetSize(t);
+	if (n == 0) return true;
+	if (tfcuda_memcpy_d2h(dst, ((TFCudaBuffer*)t->buffer)->GetNative(), n * 4) != 0)
+		throw std::runtime_error(std::string(".numpy: download failed: ") + tfcuda_last_error());
+	return true;
+}
+
+namespace {
+
+// ---- DLPack (v0.8 ABI, the subset needed for export) -----------------------------------------------------------------
+struct DLDevice { int32_t device_type; int32_t device_id; };
+struct DLDataType { uint8_t code; uint8_t bits; uint16_t lanes; };
+struct DLTensor { void* data; DLDevice device; int32_t ndim; DLDataType dtype; int64_t* shape; int64_t* strides; uint64_t byte_offset; };
+struct DLManagedTensor { DLTensor dl_tensor; void* manager_ctx; void (*deleter)(DLManagedTensor*); };
+constexpr int32_t kDLCUDA = 2;
+struct DLOwner { PyObject* tensor; std::vector<int64_t> shape; DLManagedTensor managed; };
+
+const char* TypeStr(TFDataFormat f) {
+	if (f == TFTypeFloat32) return "<f4";
+	if (f == TFTypeInt32) return "<i4";
+	if (f == TFTypeUint32) return "<u4";
+	throw std::runtime_error("device interop: only float32 / int32 / uint32 tensors are exported");
+}
+
+int CurrentDevice() { return tfcuda_device_index(); }
+
+}  // namespace
+
 namespace {
 
 void RequireCuda(const char* what) {
@@ -192,6 +250,85 @@ void CudaDefinitions(py::module& m) {
 		Check(tfcuda_memcpy_d2h(out.request().ptr, DevPtr(t), GetSize(t.tensor_) * 4), "cuda_numpy");
 		return out;
 	}, "numpy copy of a TensorMemory with one bulk copy");
+
+
+	// ---- zero-copy export of device tensors: __cuda_array_interface__ v3 and DLPack on tf.TensorMemory ----
+	{
+		py::object cls = m.attr("TensorMemory");
+		py::object property = py::module_::import("builtins").attr("property");
+		cls.attr("__cuda_array_interface__") = property(py::cpp_function([](py::object self) {
+			RequireCuda("__cuda_array_interface__");
+			const PyTensorMemory& t = self.cast<const PyTensorMemory&>();
+			py::dict d;
+			std::vector<size_t> shape = t.Shape();
+			py::tuple sh(shape.size());
+			for (size_t i = 0; i < shape.size(); i++) sh[i] = shape[i];
+			d["shape"] = sh;
+			d["typestr"] = TypeStr(t.GetFormat());
+			d["data"] = py::make_tuple((size_t)DevPtr(t), false);
+			d["strides"] = py::none();
+			d["version"] = 3;
+			d["stream"] = (size_t)reinterpret_cast<uintptr_t>(tfcuda_stream());  // consumers order themselves behind the backend stream
+			return d;
+		}));
+		cls.attr("__dlpack_device__") = py::cpp_function([](py::object) { return py::make_tuple(kDLCUDA, CurrentDevice()); }, py::is_method(cls));
+		cls.attr("__dlpack__") = py::cpp_function([](py::object self, py::object stream) -> py::capsule {
+			RequireCuda("__dlpack__");
+			(void)stream;
+			CudaFinish();  // the consumer may use any stream: hand over finished data
+			const PyTensorMemory& t = self.cast<const PyTensorMemory&>();
+			DLOwner* owner = new DLOwner();
+			owner->tensor = self.ptr();
+			Py_INCREF(owner->tensor);  // the exported view keeps the TensorMemory (and its device buffer) alive
+			for (size_t d : t.Shape()) owner->shape.push_back((int64_t)d);
+			DLTensor& dl = owner->managed.dl_tensor;
+			dl.data = reinterpret_cast<void*>(DevPtr(t));
+			dl.device = {kDLCUDA, CurrentDevice()};
+			dl.ndim = (int32_t)owner->shape.size();
+			TFDataFormat f = t.GetFormat();
+			(void)TypeStr(f);
+			dl.dtype = {(uint8_t)(f == TFTypeFloat32 ? 2 : (f == TFTypeInt32 ? 0 : 1)), 32, 1};
+			dl.shape = owner->shape.data();
+			dl.strides = nullptr;
+			dl.byte_offset = 0;
+			owner->managed.manager_ctx = owner;
+			owner->managed.deleter = [](DLManagedTensor* mt) {
+				DLOwner* o = static_cast<DLOwner*>(mt->manager_ctx);
+				py::gil_scoped_acquire gil;
+				Py_DECREF(o->tensor);
+				delete o;
+			};
+			return py::capsule(&owner->managed, "dltensor", [](PyObject* cap) {
+				// still named "dltensor": nobody consumed it, release here; a consumer renames it to "used_dltensor" and owns the deleter
+				if (PyCapsule_IsValid(cap, "dltensor")) {
+					auto* mt = static_cast<DLManagedTensor*>(PyCapsule_GetPointer(cap, "dltensor"));
+					if (mt && mt->deleter) mt->deleter(mt);
+				}
+			});
+		}, py::is_method(cls), py::arg("stream") = py::none());
+	}
+	m.def("cuda_from_device_array", [](py::object obj) {
+		RequireCuda("cuda_from_device_array");
+		if (!py::hasattr(obj, "__cuda_array_interface__")) throw std::runtime_error("cuda_from_device_array: the object has no __cuda_array_interface__");
+		py::dict d = obj.attr("__cuda_array_interface__");
+		std::string typestr = d["typestr"].cast<std::string>();
+		TFDataFormat fmt;
+		if (typestr == "<f4") fmt = TFTypeFloat32;
+		else if (typestr == "<i4") fmt = TFTypeInt32;
+		else if (typestr == "<u4") fmt = TFTypeUint32;
+		else throw std::runtime_error("cuda_from_device_array: unsupported typestr " + typestr);
+		if (d.contains("strides") && !d["strides"].is_none()) throw std::runtime_error("cuda_from_device_array: only C-contiguous arrays");
+		std::vector<size_t> shape = d["shape"].cast<std::vector<size_t>>();
+		size_t count = 1;
+		for (size_t v : shape) count *= v;
+		if (count == 0 || shape.empty()) throw std::runtime_error("cuda_from_device_array: empty arrays are not tensors");
+		uint64_t src = d["data"].cast<py::tuple>()[0].cast<uint64_t>();
+		TFTensor* t = global_memory_manager->AllocateTensor(shape, fmt);
+		Check(tfcuda_sync(), "cuda_from_device_array");  // the producer synchronised before handing the pointer over (interface v2) or we cannot know its stream
+		Check(tfcuda_memcpy_d2d(((TFCudaBuffer*)t->buffer)->GetNative(), src, count * 4), "cuda_from_device_array");
+		return new PyTensorMemory(t);
+	}, "TensorMemory from any object exposing __cuda_array_interface__ (torch / cupy / numba device arrays) with one device-to-device copy; "
+	   "the producer must have finished writing (e.g. torch.cuda.synchronize())", py::return_value_policy::take_ownership);
 
 	// ---- data-parallel exchange -------------------------------------------------------------------
 	m.def("cuda_comm_unique_id", []() {

@@ -140,6 +140,18 @@ def main():
     p.insert_after("\tModuleDefinitions(m);\n", "\tCudaDefinitions(m);\n")
     p.save()
 
+    # 5b. bulk paths behind tf.tensor(np) and .numpy (Frontend/Python/PyTensorMemory.{cpp,h}): contiguous 4-byte arrays skip the
+    # per-element conversion; everything else falls through to the reference code
+    p = Patch(tf / "Frontend" / "Python" / "PyTensorMemory.cpp")
+    p.insert_before("PyTensorMemory::PyTensorMemory(py::array arr) {", "bool CudaBulkTensor(const py::buffer_info& info, TFTensor** out);  // Backend/Backends/CUDA/CudaPython.cpp\n\n")
+    p.insert_after("PyTensorMemory::PyTensorMemory(py::array arr) {\n    py::buffer_info info = arr.request();\n",
+                   "    if (CudaBulkTensor(info, &tensor_)) return;\n")
+    p.save()
+    p = Patch(tf / "Frontend" / "Python" / "PyTensorMemory.h")
+    p.insert_before("// Tensor wrapper for python\nclass PyTensorMemory {", "bool CudaBulkReadback(const TFTensor* t, void* dst, size_t item_size);  // Backend/Backends/CUDA/CudaPython.cpp\n\n")
+    p.insert_after("\t\tpy::array_t<T> arr(shape);\n", "\t\tif (CudaBulkReadback(tensor_, arr.request().ptr, sizeof(T))) return arr;\n")
+    p.save()
+
     # 6. build: link libtfcuda.so (found next to the module at run time) and see include/tfcuda.h
     p = Patch(tf / "CMakeLists.txt")
     p.text += (

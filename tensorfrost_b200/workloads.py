@@ -110,21 +110,22 @@ def nca_pool(pool_size, grid, channel_n):
     return pool
 
 
-# ---- C3 / C4 helpers (programs are tiny and live in tests/cases.py style; restated here for bench.py) -----------------
+# ---- C3: the reference's n-body programs (extracted like the others); C4: one-line programs written here -----------------
+def _nbody_namespace(tf):
+    text, path = _source("nbody_program.py.txt")
+    ns = {"tf": tf, "np": np}
+    exec(compile(text, path, "exec"), ns)
+    return ns
+
+
 def compile_nbody(tf):
-    """examples/Simulation/n-body-benchmark.py:16-34 (`n_body`)."""
-    def prog():
-        x = tf.input([-1, 3], tf.float32)
-        n = x.shape[0]
-        v = tf.input([n, 3], tf.float32)
-        dx = tf.unsqueeze(x, axis=1) - tf.unsqueeze(x, axis=0)
-        d2 = tf.unsqueeze(tf.sum(dx ** 2.0, axis=-1), axis=-1) + 1e-4
-        dist = tf.sqrt(d2)
-        force = tf.sum(-dx * 1.0 / (d2 * dist), axis=1)
-        dt = 0.001
-        v_new = v + force * dt
-        return x + v_new * dt, v_new
-    return tf.compile(prog)
+    """examples/Simulation/n-body-benchmark.py:16-34 (`n_body`: broadcast differences + tf.sum over the partner axis)."""
+    return tf.compile(_nbody_namespace(tf)["n_body"])
+
+
+def compile_nbody_loop(tf):
+    """examples/Simulation/n-body-benchmark.py:36-65 (`n_body_loop`: one thread per body, explicit tf.loop over the partners)."""
+    return tf.compile(_nbody_namespace(tf)["n_body_loop"])
 
 
 def compile_matmul(tf):

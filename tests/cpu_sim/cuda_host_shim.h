@@ -28,6 +28,7 @@ struct sim_dim3 { unsigned x, y, z; };
 static thread_local sim_dim3 blockIdx, threadIdx, blockDim, gridDim;
 static std::barrier<>* sim_block_barrier = nullptr;  // set by the launcher of a kernel that uses barriers
 
+static inline float __fdiv_rn(float a, float b) { return a / b; }  // IEEE division on the host anyway
 static inline float __uint_as_float(unsigned v) { float f; std::memcpy(&f, &v, 4); return f; }
 static inline float __int_as_float(int v) { float f; std::memcpy(&f, &v, 4); return f; }
 static inline unsigned __float_as_uint(float f) { unsigned v; std::memcpy(&v, &f, 4); return v; }

@@ -41,7 +41,14 @@ def main():
     nca = open(os.path.join(REF, "examples", "ML", "NCA", "nca.py")).read()
     with open(os.path.join(OUT, "nca_program.py.txt"), "w") as f:
         f.write(nca)
-    print(f"[workloads] extracted fluid + NCA programs into {OUT}")
+    # the two n-body programs of examples/Simulation/n-body-benchmark.py:16-65 (the file itself imports torch / jax and opens a window)
+    src = open(os.path.join(REF, "examples", "Simulation", "n-body-benchmark.py")).read()
+    start, end = src.index("def n_body():"), src.index("def n_body_torch(")
+    body = src[start:end]
+    assert "def n_body_loop():" in body and "tf.loop(N)" in body
+    with open(os.path.join(OUT, "nbody_program.py.txt"), "w") as f:
+        f.write(body)
+    print(f"[workloads] extracted fluid + NCA + n-body programs into {OUT}")
 
 
 if __name__ == "__main__":
