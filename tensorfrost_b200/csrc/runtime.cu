@@ -47,7 +47,7 @@ State& state() {
 // the runtime stream for work issued directly (copies, memsets, allocations, events): recorded launches go first
 static cudaStream_t S() {
 	flush_recorded();
-	return S();
+	return g_state.stream;
 }
 
 void set_error(const std::string& msg) {

@@ -204,7 +204,8 @@ void CudaDefinitions(py::module& m) {
 	      "Order the backend stream behind every upload started so far (no host wait)");
 	// a download in flight keeps its source tensor (and destination array) alive: references are parked here with the download's
 	// ticket and dropped once the copy engine reports it complete
-	static std::deque<std::tuple<uint64_t, py::object, py::object>> in_flight;
+	// (heap-allocated and never destroyed: python objects must not be released after the interpreter has shut down)
+	static auto& in_flight = *new std::deque<std::tuple<uint64_t, py::object, py::object>>();
 	auto release_done = [](bool all) {
 		uint64_t done = all ? UINT64_MAX : tfcuda_downloads_done();
 		while (!in_flight.empty() && std::get<0>(in_flight.front()) <= done) in_flight.pop_front();
