@@ -12,8 +12,10 @@
 //      atomics, then one global atomic per bin), 2. scan_histogram_kernel turns them into exclusive
 //      digit offsets, 3. per pass, onesweep_kernel: each CTA takes an 8192-key tile by atomic ticket,
 //      ranks its keys stably with __match_any_sync warp multi-split, resolves its per-digit tile offset
-//      by decoupled look-back (one warp per digit reads 32 predecessor descriptors per step), stages the tile
+//      by decoupled look-back (256 digits = 256 threads looking back in parallel), stages the tile
 //      digit-sorted in shared memory and writes runs of equal digit to consecutive global addresses.
+//      (Round 2 tried a warp-per-digit look-back over a digit-major descriptor table, 32 predecessors per step: 12.75 ms instead of
+//      10.44 ms for 2^28 keys on the B200 - the serial walk is short in practice and the extra barriers cost more; reverted.)
 // Traffic per pass: n*4 B read + n*4 B written for keys (same again for values) — the minimum for an
 // out-of-place pass — plus the 1 KB/tile look-back descriptors (3%).  Keys-only, 4 passes:
 // (1 + 2*4)*4 = 36 B/key.
@@ -106,9 +108,8 @@ struct PassArgs {
 	int mode_in;   // key bijection applied when loading (first pass only)
 	int mode_out;  // inverse bijection applied when storing (last pass only)
 	const unsigned* digit_base;  // [256] exclusive global offsets of this pass
-	unsigned* desc;              // [256][tiles] look-back descriptors (digit-major: the predecessors of one digit are contiguous), zero-initialised
+	unsigned* desc;              // [tiles][256] look-back descriptors, zero-initialised
 	unsigned* ticket;            // zero-initialised
-	unsigned tiles;
 };
 
 template <bool HAS_VALUES>
@@ -119,8 +120,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2) onesweep_kernel(const __grid_co
 	unsigned* s_digit_base = s_warp_hist + RS_WARPS * RS_BINS; // [256] start of each digit inside the sorted tile
 	unsigned* s_global_off = s_digit_base + RS_BINS;           // [256] global address of sorted position 0 of the digit, minus s_digit_base
 	unsigned* s_scan = s_global_off + RS_BINS;                 // [8]
-	unsigned* s_tile_count = s_scan + 32;                      // [256] keys of each digit in this tile
-	unsigned* s_vals = s_tile_count + RS_BINS;                 // [RS_TILE] when HAS_VALUES
+	unsigned* s_vals = s_scan + 32;                            // [RS_TILE] when HAS_VALUES
 	__shared__ unsigned s_tile;
 
 	if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);
@@ -174,10 +174,9 @@ __global__ void __launch_bounds__(RS_THREADS, 2) onesweep_kernel(const __grid_co
 			tile_count += c;
 		}
 		// publish the aggregate as early as possible
-		unsigned* my_desc = a.desc + (size_t)d * a.tiles + tile;
+		unsigned* my_desc = a.desc + (size_t)tile * RS_BINS + d;
 		if (tile == 0) atomicExch(my_desc, FLAG_PREFIX | tile_count);
 		else atomicExch(my_desc, FLAG_AGG | tile_count);
-		s_tile_count[d] = tile_count;
 		// exclusive scan of tile_count over the 256 digits
 		unsigned incl = tile_count;
 #pragma unroll
@@ -190,57 +189,21 @@ __global__ void __launch_bounds__(RS_THREADS, 2) onesweep_kernel(const __grid_co
 		asm volatile("bar.sync 1, 256;");
 		unsigned base = 0;
 		for (int w = 0; w < warp; w++) base += s_scan[w];
-		s_digit_base[d] = base + incl - tile_count;
-	}
-	__syncthreads();
-
-	// Decoupled look-back, one WARP per digit and 32 predecessor tiles per step: lane l reads the descriptor of tile (hi - l) - the
-	// digit-major layout makes that one 128-byte line - so walking back W tiles costs ceil(W/32) memory round trips instead of W
-	// dependent ones.  Each of the 16 warps owns 16 digits, in two batches of 8 whose loads are issued before any is examined.
-	if (tile > 0) {
-		constexpr int PER_WARP = RS_BINS / RS_WARPS;  // 16
-		constexpr int BATCH = 8;
-#pragma unroll 1
-		for (int b0 = 0; b0 < PER_WARP; b0 += BATCH) {
-			const int d0 = warp * PER_WARP + b0;
-			unsigned open = (1u << BATCH) - 1u;  // digits of the batch whose prefix is not yet known (warp-uniform)
-			unsigned excl = 0;                   // lane j accumulates the exclusive prefix of digit d0 + j
-			for (long hi = (long)tile - 1; open != 0u; hi -= 32) {
-				const long t = hi - lane;
-				unsigned v[BATCH];
-#pragma unroll
-				for (int j = 0; j < BATCH; j++) {
-					v[j] = FLAG_PREFIX;  // before tile 0: an empty prefix
-					if (((open >> j) & 1u) && t >= 0) v[j] = *reinterpret_cast<const volatile unsigned*>(a.desc + (size_t)(d0 + j) * a.tiles + t);
-				}
-#pragma unroll
-				for (int j = 0; j < BATCH; j++) {
-					if (!((open >> j) & 1u)) continue;
-					const volatile unsigned* p = a.desc + (size_t)(d0 + j) * a.tiles + (t >= 0 ? t : 0);
-					unsigned need, pre;
-					for (;;) {
-						const unsigned pub = __ballot_sync(0xffffffffu, (v[j] & ~VALUE_MASK) != 0u);
-						pre = __ballot_sync(0xffffffffu, (v[j] & ~VALUE_MASK) == FLAG_PREFIX);
-						need = pre ? ((1u << (__ffs((int)pre) - 1)) - 1u) : 0xffffffffu;  // everything closer than the nearest prefix
-						if ((pub & need) == need) break;
-						if ((v[j] & ~VALUE_MASK) == 0u) v[j] = *p;
-					}
-					const int nearest = pre ? __ffs((int)pre) - 1 : 32;
-					unsigned contrib = lane <= nearest ? (v[j] & VALUE_MASK) : 0u;
-#pragma unroll
-					for (int off = 16; off > 0; off >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, off);
-					if (lane == j) excl += contrib;
-					if (pre) open &= ~(1u << j);
-				}
+		unsigned digit_start = base + incl - tile_count;
+		s_digit_base[d] = digit_start;
+		// decoupled look-back over predecessor tiles for this digit
+		unsigned excl = 0;
+		if (tile > 0) {
+			for (long t = (long)tile - 1; t >= 0; t--) {
+				const volatile unsigned* p = a.desc + (size_t)t * RS_BINS + d;
+				unsigned v;
+				do { v = *p; } while ((v & ~VALUE_MASK) == 0u);
+				excl += v & VALUE_MASK;
+				if ((v & ~VALUE_MASK) == FLAG_PREFIX) break;
 			}
-			if (lane < BATCH) {
-				const int d = d0 + lane;
-				atomicExch(a.desc + (size_t)d * a.tiles + tile, FLAG_PREFIX | (excl + s_tile_count[d]));
-				s_global_off[d] = a.digit_base[d] + excl - s_digit_base[d];
-			}
+			atomicExch(my_desc, FLAG_PREFIX | (excl + tile_count));
 		}
-	} else if (threadIdx.x < RS_BINS) {
-		s_global_off[threadIdx.x] = a.digit_base[threadIdx.x] - s_digit_base[threadIdx.x];
+		s_global_off[d] = a.digit_base[d] + excl - digit_start;
 	}
 	__syncthreads();
 
@@ -277,7 +240,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2) onesweep_kernel(const __grid_co
 }
 
 constexpr size_t smem_bytes(bool has_values) {
-	return (size_t)(RS_TILE + RS_WARPS * RS_BINS + RS_BINS + RS_BINS + 32 + RS_BINS + (has_values ? RS_TILE : 0)) * 4;
+	return (size_t)(RS_TILE + RS_WARPS * RS_BINS + RS_BINS + RS_BINS + 32 + (has_values ? RS_TILE : 0)) * 4;
 }
 
 size_t tiles_of(size_t n) { return (n + RS_TILE - 1) / RS_TILE; }
@@ -349,7 +312,6 @@ extern "C" int tfcuda_radix_sort(uint64_t keys_in, uint64_t keys_out, uint64_t v
 		a.digit_base = hist + p * RS_BINS;
 		a.desc = desc + (size_t)p * tiles * RS_BINS;
 		a.ticket = tickets + p;
-		a.tiles = (unsigned)tiles;
 		tfcuda::ProfileScope prof("lib/radix_onesweep", (has_values ? 16.0 : 8.0) * n);
 		if (has_values) onesweep_kernel<true><<<(unsigned)tiles, RS_THREADS, smem_bytes(true), s.stream>>>(a);
 		else onesweep_kernel<false><<<(unsigned)tiles, RS_THREADS, smem_bytes(false), s.stream>>>(a);

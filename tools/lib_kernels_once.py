@@ -35,5 +35,10 @@ nb = 32768 if quick else (65536 if medium else 262144)
 x = tf.cuda_tensor((5.0 * rng.standard_normal((nb, 3))).astype(np.float32))
 v = tf.cuda_tensor(np.zeros((nb, 3), np.float32))
 tf.cuda_nbody_step(x, v)
+ns = 1 << (20 if quick else 24)
+dst = tf.cuda_tensor(np.zeros(1 << 20, np.float32))
+idx = tf.cuda_tensor(rng.integers(0, 1 << 20, ns, dtype=np.int64).astype(np.int32))
+src = tf.cuda_tensor(rng.random(ns, dtype=np.float32))
+tf.cuda_scatter_add(dst, idx, src)
 tf.cuda_synchronize()
 print("ran", tf.cuda_launch_count(), "launches")
