@@ -834,6 +834,9 @@ def main():
     ap.add_argument("--nca-pool", type=int, default=1024)
     ap.add_argument("--nca-steps", type=int, default=25, help="CA steps per training iteration")
     ap.add_argument("--nca-iters", type=int, default=8, help="timed iterations of the 1-GPU NCA point in the N = 1 line")
+    ap.add_argument("--nca-matmul", default="tf32", choices=["tf32", "3xtf32", "fp32"],
+                    help="precision of the NCA programs' matmuls (tf.initialize option --tf-matmul): tf32 = one tensor-core product, inside "
+                         "north_star's 1e-3 matmul / gradient bar (tests/test_nca_gpu.py passes in this mode); 3xtf32 = the backend's default")
     ap.add_argument("--nca-profile", action="store_true", help="add a per-kernel profile of one iteration to the NCA line")
     ap.add_argument("--nca-mono", action="store_true", help="run the reference's single program instead of the split step (1 GPU only)")
     args = ap.parse_args()

@@ -333,8 +333,9 @@ def bench_main(args):
         args.nca_pool *= world
     sys.path.insert(0, REPO_ROOT)
     from bench import ClockSampler, quiet_stdout  # nvidia-smi clocks / throttle reasons of THIS rank's GPU during the timed region
+    matmul = getattr(args, "nca_matmul", "tf32")
     with quiet_stdout():
-        tf = tensorfrost_b200.load()
+        tf = tensorfrost_b200.load((os.environ.get("TFCUDA_KERNEL_OPTIONS", "") + " --tf-matmul=" + matmul).strip())
         method = init_comm(tf, rank, world)
         t0 = time.perf_counter()
         tr = NcaTrainer(tf, global_batch=args.nca_batch, grid=args.nca_grid, pool_size=args.nca_pool, train_steps=args.nca_steps,
@@ -438,7 +439,9 @@ def bench_main(args):
                        "per_rank_batch": args.nca_batch // world,
                        "exchange": {"peer": "one-shot allreduce kernel over NVLink peer memory (7821 fp32, rank-order sum) on the runtime stream",
                                     "nccl": "ncclAllReduce(sum) of 7821 fp32 + scale, stream drained around it", "none": "none (1 GPU)"}[method],
-                       "program": "reference single program" if args.nca_mono else "grad program -> allreduce -> apply program"},
+                       "program": "reference single program" if args.nca_mono else "grad program -> allreduce -> apply program",
+                       "matmul": {"tf32": "tf.initialize(tf.cuda, '--tf-matmul=tf32'): one tcgen05 kind::tf32 product per matmul (1e-3 class)",
+                                  "3xtf32": "backend default: 3xTF32 split products (fp32-accurate)", "fp32": "FFMA kernel"}[matmul]},
             "gpu_launches": int(launches), "loss_after": loss, "build_seconds": build_s, "clocks": clocks,
             "host_issue_ms_per_step": host_issue_ms / args.steps, "device_alloc_calls_per_step": driver_calls / args.steps, "graph": graph,
             "host_cores": os.cpu_count(),
