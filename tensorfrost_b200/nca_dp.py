@@ -261,6 +261,10 @@ class NcaTrainer:
     def parameters_numpy(self):
         return [np.array(p.numpy) for p in self.opt.parameters()]
 
+    def replicated_numpy(self):
+        """What must be bit-identical on every rank: the model's trainable tensors (the per-rank RNG seed is NOT: it is offset by rank)."""
+        return [np.array(getattr(self.model, name).numpy) for name in ("fc1", "fc1_bias", "fc2", "fc2_bias")]
+
 
 # ----------------------------------------------------------------------------------------------------------------------
 # communicator bootstrap: the NCCL unique id travels through torch.distributed's rendezvous store
@@ -359,7 +363,7 @@ def bench_main(args):
         if not args.nca_mono:
             import hashlib
             h = hashlib.sha256()
-            for p in tr.parameters_numpy():
+            for p in tr.replicated_numpy():
                 h.update(np.ascontiguousarray(p).tobytes())
             digest = h.hexdigest()
         phase_ms = None
