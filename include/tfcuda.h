@@ -203,7 +203,8 @@ typedef struct TFCudaGraphStats {
 	uint64_t exact_hits;      /* ... that reused an executable graph unchanged */
 	uint64_t patched;         /* ... whose kernel arguments were patched in place */
 	uint64_t instantiated;    /* ... that needed a new executable graph */
-	uint64_t eager_launches;  /* kernels of short chains launched one by one */
+	uint64_t eager_launches;  /* kernels of short or never-repeating chains launched one by one */
+	double host_us;           /* host time spent issuing recorded chains so far (graph upkeep + launches) */
 } TFCudaGraphStats;
 int tfcuda_graph_begin(void);
 int tfcuda_graph_end(void);

@@ -39,7 +39,7 @@ class TFCudaKernelSource(C.Structure):
 
 
 class TFCudaGraphStats(C.Structure):
-    _fields_ = [("enabled", C.c_int), ("replays", u64), ("exact_hits", u64), ("patched", u64), ("instantiated", u64), ("eager_launches", u64)]
+    _fields_ = [("enabled", C.c_int), ("replays", u64), ("exact_hits", u64), ("patched", u64), ("instantiated", u64), ("eager_launches", u64), ("host_us", C.c_double)]
 
 
 class TFCudaProfileRecord(C.Structure):

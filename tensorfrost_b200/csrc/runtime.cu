@@ -17,6 +17,7 @@
 #include <unistd.h>
 
 #include <atomic>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -549,6 +550,8 @@ struct GraphExec {
 struct GraphShape {
 	std::vector<RecOp> ops;  // arg_offset / arg_bytes included: equal shapes have equal layouts
 	std::vector<GraphExec> execs;
+	uint32_t hits = 0, misses = 0;  // exact replays vs executions that needed a new or patched executable graph
+	bool eager = false;             // the arguments of this chain keep changing: graph bookkeeping costs more than it saves
 };
 struct Recorder {
 	int depth = 0;            // tfcuda_graph_begin nesting
@@ -560,6 +563,7 @@ struct Recorder {
 	std::unordered_map<uint64_t, GraphShape> shapes;
 	uint64_t tick = 0;
 	uint64_t replays = 0, exact_hits = 0, patched = 0, instantiated = 0, eager = 0;
+	double host_us = 0.0;     // host time spent issuing recorded chains (hashing, graph upkeep, launches)
 	std::string error;        // first failure of a deferred launch; reported by the next tfcuda_launch / tfcuda_graph_end / tfcuda_sync
 };
 static Recorder g_rec;
@@ -661,6 +665,7 @@ static void flush_recorded() {
 	args.swap(R.args);
 	const size_t n = ops.size();
 	bool done = false;
+	const auto t_begin = std::chrono::steady_clock::now();
 	if (n >= kMinGraphOps && R.error.empty()) {
 		const uint64_t shape_hash = hash_bytes(ops.data(), n * sizeof(RecOp));
 		const uint64_t args_hash = hash_bytes(args.data(), args.size());
@@ -681,9 +686,23 @@ static void flush_recorded() {
 			if (ge.args_hash == args_hash && ge.args.size() == args.size() && memcmp(ge.args.data(), args.data(), args.size()) == 0) {
 				use = &ge;
 				R.exact_hits++;
+				gs.hits++;
 				break;
 			}
-		if (!use && gs.execs.size() < kExecsPerShape) {
+		// Adaptive: a chain whose arguments keep changing (the pool hands its buffers out in a different order every time: NCA training
+		// steps) pays for instantiation / node patching on every execution and never replays; after a trial period such chains are
+		// launched eagerly for good.  Chains that do repeat (the fluid step: two alternating address sets) stay on the graph path.
+		if (!use) {
+			gs.misses++;
+			if (!gs.eager && gs.misses >= 8 && gs.hits < gs.misses) {
+				gs.eager = true;
+				for (GraphExec& ge : gs.execs) destroy_exec(ge);
+				gs.execs.clear();
+			}
+		}
+		if (gs.eager) {
+			// fall through to the eager loop below
+		} else if (!use && gs.execs.size() < kExecsPerShape) {
 			GraphExec ge;
 			if (build_exec(ge, ops, args)) {
 				ge.args_hash = args_hash;
@@ -691,7 +710,7 @@ static void flush_recorded() {
 				use = &gs.execs.back();
 				R.instantiated++;
 			}
-		} else if (!use) {
+		} else if (!use && !gs.execs.empty()) {
 			GraphExec* lru = &gs.execs[0];
 			for (GraphExec& ge : gs.execs)
 				if (ge.last_used < lru->last_used) lru = &ge;
@@ -729,6 +748,7 @@ static void flush_recorded() {
 		R.eager += n;
 	}
 	g_state.launches += n;
+	R.host_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_begin).count();
 	R.flushing = false;
 }
 
@@ -742,7 +762,10 @@ static void recorder_reset() {
 
 using namespace tfcuda;
 
-// copy engines (tfcuda_memcpy_*_async below)
+// copy engines (tfcuda_memcpy_*_async below) and the staging ring of small uploads (tfcuda_memcpy_h2d)
+static unsigned char* g_ring = nullptr;
+static size_t g_ring_at = 0;
+static const size_t kRingBytes = 4u << 20, kRingMaxCopy = 64u << 10;
 static cudaStream_t g_up_stream = nullptr, g_down_stream = nullptr;
 static cudaEvent_t g_up_event = nullptr, g_down_event = nullptr, g_order_event = nullptr;
 static bool g_up_pending = false;
@@ -868,6 +891,9 @@ int tfcuda_shutdown(void) {
 	cudaEventDestroy(g_state.ev_begin);
 	cudaEventDestroy(g_state.ev_end);
 	cudaFreeHost(g_state.pinned_word);
+	if (g_ring) cudaFreeHost(g_ring);
+	g_ring = nullptr;
+	g_ring_at = 0;
 	if (g_up_stream) {
 		cudaStreamDestroy(g_up_stream);
 		cudaStreamDestroy(g_down_stream);
@@ -927,6 +953,7 @@ int tfcuda_graph_stats(TFCudaGraphStats* out) {
 	out->patched = g_rec.patched;
 	out->instantiated = g_rec.instantiated;
 	out->eager_launches = g_rec.eager;
+	out->host_us = g_rec.host_us;
 	return 0;
 }
 
@@ -972,9 +999,25 @@ int tfcuda_buffer_read(const TFBuffer* buffer, size_t word_offset, uint32_t* dst
 	return tfcuda_memcpy_d2h(dst, dptr_of(buffer) + word_offset * 4, words * 4);
 }
 
+// Small uploads (program parameters, batch indices: a few bytes to a few KB per call) are staged through a ring of page-locked
+// memory and copied asynchronously.  A cudaMemcpyAsync from PAGEABLE memory first synchronises the stream, so a program fed a numpy
+// scalar on every call would drain the whole pipeline once per call (one of the two stalls of a data-parallel NCA step).
+
 int tfcuda_memcpy_h2d(uint64_t dst, const void* src, size_t bytes) {
 	if (!g_state.initialized) { set_error("tfcuda: not initialised"); return 1; }
 	if (bytes == 0) return 0;
+	if (bytes <= kRingMaxCopy) {
+		if (!g_ring) TFCUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&g_ring), kRingBytes));
+		const size_t need = (bytes + 255) & ~size_t(255);
+		if (g_ring_at + need > kRingBytes) {
+			TFCUDA_CHECK(cudaStreamSynchronize(S()));  // wrap-around: every copy staged so far has left the ring
+			g_ring_at = 0;
+		}
+		memcpy(g_ring + g_ring_at, src, bytes);
+		TFCUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<void*>(dst), g_ring + g_ring_at, bytes, cudaMemcpyHostToDevice, S()));
+		g_ring_at += need;
+		return 0;
+	}
 	TFCUDA_CHECK(cudaMemcpyAsync(reinterpret_cast<void*>(dst), src, bytes, cudaMemcpyHostToDevice, S()));
 	// pageable sources are consumed before the call returns; pinned ones are not, so order the host too
 	TFCUDA_CHECK(cudaStreamSynchronize(S()));

@@ -236,6 +236,7 @@ void CudaDefinitions(py::module& m) {
 		d["patched"] = st.patched;
 		d["instantiated"] = st.instantiated;
 		d["eager_launches"] = st.eager_launches;
+		d["host_ms"] = st.host_us / 1e3;
 		return d;
 	}, "Counters of the launch recorder (graph replay of program dispatch chains)");
 
