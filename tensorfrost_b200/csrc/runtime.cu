@@ -694,7 +694,7 @@ static void flush_recorded() {
 		// launched eagerly for good.  Chains that do repeat (the fluid step: two alternating address sets) stay on the graph path.
 		if (!use) {
 			gs.misses++;
-			if (!gs.eager && gs.misses >= 8 && gs.hits < gs.misses) {
+			if (!gs.eager && ((gs.misses >= 5 && gs.hits == 0) || (gs.misses >= 12 && gs.hits < gs.misses))) {
 				gs.eager = true;
 				for (GraphExec& ge : gs.execs) destroy_exec(ge);
 				gs.execs.clear();
