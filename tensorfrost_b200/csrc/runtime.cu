@@ -86,8 +86,10 @@ static size_t round_words(size_t words) { return (words + 63) & ~size_t(63); }
 // (Compiler/Implementations.cpp:293) and the clamp is lost: e.g. NCA's max_neighbor_alpha (examples/ML/NCA/nca.py:45-48) reads one
 // image row before / after its tensor, on the reference's own C++ backend too.  What such a read returns is whatever lies next to
 // the tensor, so results would depend on the allocation history of the process.  Every tensor buffer therefore sits between two
-// zero-filled bands (zeroed once, when the buffer is created; emitted kernels never write out of range): reads that overshoot by
-// less than the band see zeros - the value a fresh heap gives the reference - independent of what ran before.
+// zero-filled bands (zeroed once, when the buffer is created; emitted kernels never write out of range): reads that overshoot the
+// BUFFER by less than the band see zeros - the value a fresh heap gives the reference - independent of what ran before.  (The
+// reference pool above may hand a tensor a recycled buffer up to 16x larger than it needs, TensorMemory.cpp:186-213: an overshoot past
+// the tensor but inside such a buffer reads the previous tenant's data, on this backend as on the reference's.)
 static size_t guard_bytes() {
 	static const size_t g = [] {
 		const char* v = getenv("TFCUDA_GUARD_BYTES");

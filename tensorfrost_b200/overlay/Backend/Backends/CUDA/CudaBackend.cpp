@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
+#include <unordered_map>
 
 #include "CUDA.h"
 #include "Backend/Backend.h"
@@ -169,7 +170,12 @@ bool CudaHostProgramCache(const std::string& code, const char* dll_name, size_t 
 	return true;
 }
 
+// kernel id -> number of read-write bindings (the read-only ones follow, Compiler/KernelGen.h:36-45).  Read-only bindings are declared
+// `const uint* __restrict__` in emitted kernels (a no-alias promise to the compiler); DispatchKernel checks the promise.
+static std::unordered_map<size_t, size_t> g_rw_count;
+
 void CudaKernelManager::CompileProgram(Program* program) {
+	for (auto& kernel : program->kernels_) g_rw_count[kernel.kernel_id_] = kernel.read_write_memory.size();
 	vector<TFCudaKernelSource> sources;
 	sources.reserve(program->kernels_.size());
 	for (auto& kernel : program->kernels_) {
@@ -199,6 +205,17 @@ void CudaKernelManager::DispatchKernel(TFDispatchInfo info) {
 	if (info.read_write_count > 256) throw std::runtime_error("CUDA backend: too many buffers in dispatch");
 	for (size_t i = 0; i < info.read_write_count; i++) {
 		ptrs[i] = ((TFCudaBuffer*)info.read_write_tensors[i].buffer)->GetNative();
+	}
+	// A read-only binding that is the same device buffer as a writable one (a reshape view of a tensor the kernel also writes, or one
+	// TensorMemory passed as two program inputs) would break the __restrict__ promise of the emitted kernel: refuse loudly.
+	auto rw = g_rw_count.find(info.kernel_id);
+	static const bool no_restrict = cudaKernelCompileOptions.find("TF_NO_RESTRICT") != std::string::npos || getenv("TFCUDA_RO") != nullptr;
+	if (rw != g_rw_count.end() && !no_restrict) {
+		for (size_t i = rw->second; i < info.read_write_count; i++)
+			for (size_t j = 0; j < rw->second && j < info.read_write_count; j++)
+				if (ptrs[i] == ptrs[j])
+					throw std::runtime_error("CUDA backend: kernel " + std::to_string(info.kernel_id) + " binds one device buffer both read-only and writable; "
+					                         "initialise with tf.initialize(tf.cuda, \"-DTF_NO_RESTRICT\") (or TFCUDA_RO=0 at trace time) for such programs");
 	}
 	// algorithmic traffic of this dispatch = every bound tensor once (only accounted while profiling)
 	double bytes = 0;

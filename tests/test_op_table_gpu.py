@@ -116,3 +116,25 @@ extern "C" __global__ void __launch_bounds__(256) kernel_900001(const __grid_con
     value = (x >= 0.25).astype(np.float32) + np.float32(2.0) * np.trunc(x * np.float32(3.5))
     want = np.where(x < -0.5, np.float32(7.0), value)  # discarded threads leave the output untouched
     assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+def test_aliased_read_only_and_writable_binding_is_refused(tf_cuda):
+    """Read-only bindings are `const uint* __restrict__` in emitted kernels; binding one device buffer both read-only and writable (the
+    same TensorMemory passed as two program inputs, one of which the kernel writes) would make that promise false.  The dispatch refuses
+    it with a message naming the switch (-DTF_NO_RESTRICT) instead of computing on possibly stale loads."""
+    tf = tf_cuda
+
+    def prog():
+        a = tf.input([-1], tf.float32)
+        b = tf.input(a.shape, tf.float32)
+        i, = a.indices
+        a[i] = b[i] * 2.0 + 1.0
+        return a
+    p = tf.compile(prog)
+    x = tf.tensor(np.arange(64, dtype=np.float32))
+    y = tf.tensor(np.ones(64, dtype=np.float32))
+    out = p(x, y)
+    assert np.array_equal(np.array(out.numpy), np.full(64, 3.0, np.float32))
+    with pytest.raises(RuntimeError, match="TF_NO_RESTRICT"):
+        p(x, x)
