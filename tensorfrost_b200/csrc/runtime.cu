@@ -771,8 +771,12 @@ static const size_t kRingBytes = 4u << 20, kRingMaxCopy = 64u << 10;
 static cudaStream_t g_up_stream = nullptr, g_down_stream = nullptr;
 static cudaEvent_t g_up_event = nullptr, g_down_event = nullptr, g_order_event = nullptr;
 static bool g_up_pending = false;
-static std::atomic<uint64_t> g_down_issued{0}, g_down_done{0};
-static void CUDART_CB download_done_cb(void*) { g_down_done.fetch_add(1, std::memory_order_release); }
+// Completion of downloads is tracked with one event per download, polled by tfcuda_downloads_done().  (A cudaLaunchHostFunc callback
+// per download was measured on the B200: it stalls the copy stream for ~0.28 ms each - downloads of 4 x 16 MB took 2.32 ms instead of
+// 1.21 ms and the end-to-end fluid step 2.56 ms instead of 1.55 ms.)
+static uint64_t g_down_issued = 0, g_down_done = 0;
+static std::vector<std::pair<uint64_t, cudaEvent_t>> g_down_pending;  // (ticket, event), oldest first
+static std::vector<cudaEvent_t> g_down_event_pool;
 
 // ================================================================================================
 // C-ABI
@@ -902,6 +906,10 @@ int tfcuda_shutdown(void) {
 		cudaEventDestroy(g_up_event);
 		cudaEventDestroy(g_down_event);
 		cudaEventDestroy(g_order_event);
+		for (auto& pe : g_down_pending) cudaEventDestroy(pe.second);
+		for (cudaEvent_t e : g_down_event_pool) cudaEventDestroy(e);
+		g_down_pending.clear();
+		g_down_event_pool.clear();
 		g_up_stream = g_down_stream = nullptr;
 		g_up_pending = false;
 	}
@@ -1075,19 +1083,38 @@ int tfcuda_memcpy_d2h_async(void* dst, uint64_t src, size_t bytes) {
 	TFCUDA_CHECK(cudaStreamWaitEvent(g_down_stream, g_order_event, 0));
 	TFCUDA_CHECK(cudaMemcpyAsync(dst, reinterpret_cast<const void*>(src), bytes, cudaMemcpyDeviceToHost, g_down_stream));
 	TFCUDA_CHECK(cudaEventRecord(g_down_event, g_down_stream));
-	g_down_issued.fetch_add(1);
-	TFCUDA_CHECK(cudaLaunchHostFunc(g_down_stream, download_done_cb, nullptr));
+	cudaEvent_t ev;
+	if (!g_down_event_pool.empty()) {
+		ev = g_down_event_pool.back();
+		g_down_event_pool.pop_back();
+	} else {
+		TFCUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+	}
+	TFCUDA_CHECK(cudaEventRecord(ev, g_down_stream));
+	g_down_pending.emplace_back(++g_down_issued, ev);
 	return 0;
 }
 
-uint64_t tfcuda_downloads_issued(void) { return g_down_issued.load(); }
-uint64_t tfcuda_downloads_done(void) { return g_down_done.load(std::memory_order_acquire); }
+uint64_t tfcuda_downloads_issued(void) { return g_down_issued; }
+
+uint64_t tfcuda_downloads_done(void) {
+	size_t k = 0;
+	while (k < g_down_pending.size() && cudaEventQuery(g_down_pending[k].second) == cudaSuccess) {
+		g_down_done = g_down_pending[k].first;
+		g_down_event_pool.push_back(g_down_pending[k].second);
+		k++;
+	}
+	(void)cudaGetLastError();  // cudaErrorNotReady of the first unfinished event is not an error
+	if (k) g_down_pending.erase(g_down_pending.begin(), g_down_pending.begin() + k);
+	return g_down_done;
+}
 
 int tfcuda_copy_sync(void) {
 	if (!g_state.initialized) { set_error("tfcuda: not initialised"); return 1; }
 	if (!g_up_stream) return 0;
 	TFCUDA_CHECK(cudaStreamSynchronize(g_up_stream));
 	TFCUDA_CHECK(cudaStreamSynchronize(g_down_stream));
+	(void)tfcuda_downloads_done();  // everything issued so far has completed: recycle the events
 	return 0;
 }
 

@@ -86,6 +86,11 @@ vector<int> CudaDefaultGroupSize(int dims, const vector<int>& const_shape) {
 	const int target = 256;
 	vector<int> group;
 	int g0 = min(extent(0), dims == 1 ? target : 32);
+	// A short constant innermost extent that is not a multiple of the warp (36 filter responses, 48 concatenated channels per cell in
+	// the NCA example): take whole rows, so that consecutive thread ids are consecutive addresses across the rows of a block; 32-wide
+	// blocks would leave a second block column with 4 (or 16) of 32 lanes busy.  TFCUDA_WHOLE_ROWS=0 restores the 32-wide choice.
+	static const bool whole_rows = !(getenv("TFCUDA_WHOLE_ROWS") && atoi(getenv("TFCUDA_WHOLE_ROWS")) == 0);
+	if (whole_rows && dims >= 2 && extent(0) > 32 && extent(0) <= 96 && extent(0) % 32 != 0) g0 = extent(0);
 	group.push_back(g0);
 	if (dims == 1) return group;
 	int remaining = max(1, target / g0);
