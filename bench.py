@@ -490,7 +490,7 @@ def time_call(tf, fn, iters, warm=3):
     return tf.cuda_timer_end() / iters
 
 
-def bench_extra(tf, peaks, quick):
+def bench_extra(tf, peaks, quick, only=None):
     """BASELINE.json's other metrics at the configs' sizes, each against its own roofline, each with its timed output VERIFIED
     (sort: sortedness + stability + permutation; n-body / matmul / reductions: float64 on sampled rows) and an end-to-end figure
     (host buffers in, host buffers out).  Every section is independent: a failure is recorded under its name."""
@@ -503,6 +503,8 @@ def bench_extra(tf, peaks, quick):
     tf32_peak = peaks["bf16_tflops"] / 2
 
     def section(name, fn):
+        if only is not None and name not in only:
+            return
         try:
             fn()
         except Exception as e:  # noqa: BLE001
@@ -765,6 +767,21 @@ def cpu_extras(args):
         return {"error": f"failed: {e}"}
 
 
+def nbody_approx_leg():
+    """The reference's n-body programs once more, in a process whose kernels are compiled with approximate division / square root
+    (`tf.initialize(tf.cuda, "--prec-div=false --prec-sqrt=false")`: 2 ulp per operation, inside north_star's 1e-5; IEEE is the default)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--workload", "nbody"]
+    env = dict(os.environ, TFCUDA_KERNEL_OPTIONS="--prec-div=false --prec-sqrt=false")
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd="/tmp", env=env)
+        for line in reversed(r.stdout.strip().splitlines()):
+            if line.startswith("{"):
+                return json.loads(line)
+        return {"error": "no JSON: " + r.stderr[-200:]}
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"failed: {e}"}
+
+
 def nca_single_gpu(args):
     """The 1-GPU point of the data-parallel NCA config, in its own process (fresh pool, no interference with the fluid numbers)."""
     cmd = [sys.executable, os.path.abspath(__file__), "--workload", "nca", "--steps", str(args.nca_iters), "--warmup", "3", "--no-single"]
@@ -829,7 +846,7 @@ def main():
     ap.add_argument("--no-nca", action="store_true", help="skip the 1-GPU NCA point at N = 1")
     ap.add_argument("--no-single", action="store_true", help="NCA at N > 1: skip rank 0's single-GPU reference runs")
     ap.add_argument("--quick", action="store_true", help="smaller extra workloads (development)")
-    ap.add_argument("--workload", default=None, choices=["fluid", "nca", "extras"],
+    ap.add_argument("--workload", default=None, choices=["fluid", "nca", "extras", "nbody"],
                     help="default: fluid at N = 1, nca (the config that shards) under torchrun with N > 1")
     ap.add_argument("--verify-steps", type=int, default=10)
     ap.add_argument("--dump-state", default=None, help="reference arm: save the fields after --verify-steps steps from rest")
@@ -853,6 +870,13 @@ def main():
     if args.workload == "nca":
         from tensorfrost_b200 import nca_dp
         return nca_dp.bench_main(args)
+    if args.workload == "nbody":  # the n-body section alone (used by nbody_approx_leg with other kernel compile options)
+        import tensorfrost_b200
+        with quiet_stdout():
+            tf = tensorfrost_b200.load()
+            res = bench_extra(tf, read_peaks(), args.quick, only=("nbody",))
+        print(json.dumps(res))
+        return 0
 
     # the 1-GPU point of the data-parallel NCA config runs first, in its own process, while this one holds no device memory
     nca_line = nca_single_gpu(args) if (world == 1 and not args.no_nca) else None
@@ -877,6 +901,14 @@ def main():
                             extra[key]["cpu_baseline"] = cpu
         if nca_line is not None:
             line["nca_dp"] = nca_line
+        if extra is not None and not args.no_cpu:
+            approx = nbody_approx_leg()
+            for key in ("nbody_program", "nbody_loop_program"):
+                if key in approx:
+                    approx[key]["note"] += "; kernels compiled with --prec-div=false --prec-sqrt=false (user option of tf.initialize; IEEE is the default)"
+                    extra[key + "_approx_div_sqrt"] = approx[key]
+            if "error" in approx:
+                extra["nbody_approx_error"] = approx["error"]
         if extra is not None:
             line["extra"] = extra
             line["extra_summary"] = summarize_extra(extra)

@@ -292,6 +292,18 @@ def init_comm(tf, rank, world):
         ok = 0
     votes = [None] * world
     dist.all_gather_object(votes, ok)
+    if not all(votes):
+        dist.barrier()
+        return "nccl"
+    # every rank mapped its peers.  Self-check before the exchange is trusted: the same vector through the peer kernel and through
+    # ncclAllReduce (this also gives the NCCL communicator its first collective)
+    probe = (np.arange(1024, dtype=np.float32) * 0.25 + rank).astype(np.float32)
+    a, b = tf.cuda_tensor(probe), tf.cuda_tensor(probe)
+    tf.cuda_allreduce(a, 1.0 / world, "peer")
+    tf.cuda_allreduce(b, 1.0 / world, "nccl")
+    want = (np.arange(1024, dtype=np.float64) * 0.25 + (world - 1) / 2.0)
+    ok = int(np.allclose(tf.cuda_numpy(a), want, rtol=1e-6) and np.allclose(tf.cuda_numpy(a), tf.cuda_numpy(b), rtol=1e-6))
+    dist.all_gather_object(votes, ok)
     dist.barrier()
     return "peer" if all(votes) else "nccl"
 

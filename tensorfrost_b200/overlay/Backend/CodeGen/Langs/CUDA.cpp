@@ -164,7 +164,12 @@ void GenerateCUDAKernel(Program* program, Kernel* kernel) {
 	if (n_mem > 0) bindings += "  uint* mem[" + to_string(n_mem) + "];\n";
 	bindings += "  uint var[" + to_string(n_var) + "];\n};\n";
 
-	string main_code = "extern \"C\" __global__ void __launch_bounds__(" + to_string(threads) + ") " + kname +
+	// TFCUDA_MIN_BLOCKS=n (tuning aid): ask for n resident blocks per SM, i.e. cap the registers per thread at 65536 / (n * threads)
+	string bounds = to_string(threads);
+	if (const char* mb = getenv("TFCUDA_MIN_BLOCKS")) {
+		if (atoi(mb) > 0) bounds += ", " + to_string(atoi(mb));
+	}
+	string main_code = "extern \"C\" __global__ void __launch_bounds__(" + bounds + ") " + kname +
 	                   "(const __grid_constant__ " + args_t + " tf_a)\n{\n";
 	main_code += GetGroupBufferDeclarations(kernel, CudaSharedDeclaration);
 	// read-only bindings (Kernel::read_only_memory come after the rw ones, KernelGen.h:36-45) are declared through TF_RO
