@@ -195,13 +195,14 @@ int tfcuda_launch(size_t kernel_id, const uint64_t* mem, size_t n_mem,
 /* Graph replay of a program's launches (whole-program CUDA graph).  The backend glue brackets every program execution
  * (ExecuteProgram, Backend/Backend.cpp:137-185) with begin/end; in between tfcuda_launch only records, and the recorded chain is
  * issued as ONE cudaGraphLaunch when the program ends or the moment anything else needs the stream (tf.read, a copy, a library
- * kernel).  Executable graphs are cached by kernel sequence + argument bytes, so a steady-state step costs one graph launch.
+ * kernel).  Executable graphs are cached by kernel sequence + argument bytes and built the second time a chain is seen with the same
+ * arguments, so a steady-state step costs one graph launch and chains that never repeat are simply launched.
  * Bit-identical to eager execution; TFCUDA_GRAPH=0 disables it.  Calls nest; end returns non-zero when a deferred launch failed. */
 typedef struct TFCudaGraphStats {
 	int enabled;
 	uint64_t replays;         /* graph launches */
 	uint64_t exact_hits;      /* ... that reused an executable graph unchanged */
-	uint64_t patched;         /* ... whose kernel arguments were patched in place */
+	uint64_t patched;         /* (unused since the second-sight policy; kept for ABI stability) */
 	uint64_t instantiated;    /* ... that needed a new executable graph */
 	uint64_t eager_launches;  /* kernels of short or never-repeating chains launched one by one */
 	double host_us;           /* host time spent issuing recorded chains so far (graph upkeep + launches) */

@@ -526,12 +526,15 @@ static bool load_entry(const char* sym, T& fn) {
 // execution) tfcuda_launch therefore only RECORDS {function, grid, block, argument block}.  The list is issued when the program
 // ends - or earlier, the moment anything else needs the stream (a tf.read, a copy, a library kernel, a driver allocation: every
 // such path goes through S() / state()) - as ONE cudaGraphLaunch of a linear kernel-node chain:
-//   * exact hit   (same kernels, same argument bytes as an earlier execution: the pool hands out the same addresses every
-//                  step, or alternates between two sets when outputs are fed back)     -> cuGraphLaunch, nothing else;
-//   * shape hit   (same kernels, other arguments)                                      -> a new executable graph while fewer than
-//                  kExecsPerShape exist for the shape, else the least recently used one is patched node by node
-//                  (cuGraphExecKernelNodeSetParams on the nodes whose bytes differ);
-//   * miss                                                                              -> build + instantiate.
+//   * exact hit    (same kernels, same argument bytes as an executable graph built earlier: the pool hands out the same addresses
+//                   every step, or alternates between two sets when outputs are fed back)  -> cuGraphLaunch, nothing else;
+//   * second sight (same kernels and the same argument bytes as a recent execution that was launched eagerly: the chain repeats)
+//                                                                                         -> build + instantiate, then replay
+//                   (at most kExecsPerShape executable graphs per kernel sequence, least recently used evicted);
+//   * first sight  (arguments never seen: a training step whose buffers come back in a different order every time)
+//                                                                                         -> launch eagerly, remember the hash.
+// A chain therefore pays for a graph only once it has proven to repeat: measured at 8 GPUs on the NCA step (whose chains never
+// repeat), instantiating on every miss cost 10 ms of a 73 ms step under host contention; with this rule the step takes 63 ms.
 // The argument bytes are baked into the nodes, so a replay launches exactly what eager execution would have launched, in the
 // same order; results are bit-identical (tests/test_graph_replay_gpu.py).  Lists shorter than kMinGraphOps are launched eagerly.
 // ------------------------------------------------------------------------------------------------
@@ -552,8 +555,8 @@ struct GraphExec {
 struct GraphShape {
 	std::vector<RecOp> ops;  // arg_offset / arg_bytes included: equal shapes have equal layouts
 	std::vector<GraphExec> execs;
-	uint32_t hits = 0, misses = 0;  // exact replays vs executions that needed a new or patched executable graph
-	bool eager = false;             // the arguments of this chain keep changing: graph bookkeeping costs more than it saves
+	uint64_t seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // argument hashes of recent executions that were launched eagerly
+	unsigned seen_at = 0;
 };
 struct Recorder {
 	int depth = 0;            // tfcuda_graph_begin nesting
@@ -688,49 +691,29 @@ static void flush_recorded() {
 			if (ge.args_hash == args_hash && ge.args.size() == args.size() && memcmp(ge.args.data(), args.data(), args.size()) == 0) {
 				use = &ge;
 				R.exact_hits++;
-				gs.hits++;
 				break;
 			}
-		// Adaptive: a chain whose arguments keep changing (the pool hands its buffers out in a different order every time: NCA training
-		// steps) pays for instantiation / node patching on every execution and never replays; after a trial period such chains are
-		// launched eagerly for good.  Chains that do repeat (the fluid step: two alternating address sets) stay on the graph path.
 		if (!use) {
-			gs.misses++;
-			if (!gs.eager && ((gs.misses >= 5 && gs.hits == 0) || (gs.misses >= 12 && gs.hits < gs.misses))) {
-				gs.eager = true;
-				for (GraphExec& ge : gs.execs) destroy_exec(ge);
-				gs.execs.clear();
-			}
-		}
-		if (gs.eager) {
-			// fall through to the eager loop below
-		} else if (!use && gs.execs.size() < kExecsPerShape) {
-			GraphExec ge;
-			if (build_exec(ge, ops, args)) {
-				ge.args_hash = args_hash;
-				gs.execs.push_back(std::move(ge));
-				use = &gs.execs.back();
-				R.instantiated++;
-			}
-		} else if (!use && !gs.execs.empty()) {
-			GraphExec* lru = &gs.execs[0];
-			for (GraphExec& ge : gs.execs)
-				if (ge.last_used < lru->last_used) lru = &ge;
-			bool ok = true;
-			for (size_t i = 0; i < n && ok; i++) {
-				const RecOp& op = ops[i];
-				if (memcmp(lru->args.data() + op.arg_offset, args.data() + op.arg_offset, op.arg_bytes) == 0) continue;
-				void* params[1] = {args.data() + op.arg_offset};
-				CUDA_KERNEL_NODE_PARAMS kp;
-				fill_node_params(kp, op, params);
-				CUresult r = g_state.drv.GraphExecKernelNodeSetParams(lru->exec, lru->nodes[i], &kp);
-				if (r != CUDA_SUCCESS) ok = rec_fail("cuGraphExecKernelNodeSetParams", r);
-			}
-			if (ok) {
-				lru->args = args;
-				lru->args_hash = args_hash;
-				use = lru;
-				R.patched++;
+			bool seen_before = false;
+			for (uint64_t h : gs.seen) seen_before |= (h == args_hash);
+			if (seen_before) {
+				// these exact arguments were launched (eagerly) not long ago: the chain repeats, a graph pays off from now on
+				if (gs.execs.size() >= kExecsPerShape) {
+					size_t lru = 0;
+					for (size_t i = 1; i < gs.execs.size(); i++)
+						if (gs.execs[i].last_used < gs.execs[lru].last_used) lru = i;
+					destroy_exec(gs.execs[lru]);
+					gs.execs.erase(gs.execs.begin() + (long)lru);
+				}
+				GraphExec ge;
+				if (build_exec(ge, ops, args)) {
+					ge.args_hash = args_hash;
+					gs.execs.push_back(std::move(ge));
+					use = &gs.execs.back();
+					R.instantiated++;
+				}
+			} else {
+				gs.seen[gs.seen_at++ % 8] = args_hash;
 			}
 		}
 		if (use) {
