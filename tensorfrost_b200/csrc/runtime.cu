@@ -536,7 +536,8 @@ static bool load_entry(const char* sym, T& fn) {
 // A chain therefore pays for a graph only once it has proven to repeat: measured at 8 GPUs on the NCA step (whose chains never
 // repeat), instantiating on every miss cost 10 ms of a 73 ms step under host contention; with this rule the step takes 63 ms.
 // The argument bytes are baked into the nodes, so a replay launches exactly what eager execution would have launched, in the
-// same order; results are bit-identical (tests/test_graph_replay_gpu.py).  Lists shorter than kMinGraphOps are launched eagerly.
+// same order; results are bit-identical (tests/test_graph_replay_gpu.py).  Lists shorter than kMinGraphOps, and lists without at least
+// kMinGraphOps launch-latency-sized kernels, are launched eagerly.
 // ------------------------------------------------------------------------------------------------
 struct RecOp {
 	CUfunction fn;
@@ -573,6 +574,7 @@ struct Recorder {
 };
 static Recorder g_rec;
 static const size_t kMinGraphOps = 4;
+static const uint64_t kSmallKernelThreads = 1ull << 21;  // below ~2 M threads a kernel on 148 SMs is over in a few microseconds
 static const size_t kExecsPerShape = 4;
 static const size_t kMaxShapes = 256;
 
@@ -671,7 +673,12 @@ static void flush_recorded() {
 	const size_t n = ops.size();
 	bool done = false;
 	const auto t_begin = std::chrono::steady_clock::now();
-	if (n >= kMinGraphOps && R.error.empty()) {
+	// What a graph saves is launch latency, so it only pays for chains of SHORT kernels (the 3-6 us multigrid sweeps of the fluid
+	// step); a chain of kernels with millions of threads each (an NCA training step) is device-bound whatever the launch path is,
+	// and graph upkeep would only add host work.  A chain qualifies when at least kMinGraphOps of its kernels are small.
+	size_t small_ops = 0;
+	for (const RecOp& op : ops) small_ops += ((uint64_t)op.grid * op.block[0] * op.block[1] * op.block[2] < kSmallKernelThreads) ? 1 : 0;
+	if (n >= kMinGraphOps && small_ops >= kMinGraphOps && R.error.empty()) {
 		const uint64_t shape_hash = hash_bytes(ops.data(), n * sizeof(RecOp));
 		const uint64_t args_hash = hash_bytes(args.data(), args.size());
 		if (R.shapes.size() >= kMaxShapes && !R.shapes.count(shape_hash)) {

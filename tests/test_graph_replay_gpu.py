@@ -63,7 +63,7 @@ def test_replay_is_bit_identical_to_eager_and_hits_after_warmup(tmp_path):
     assert s1["enabled"] and s1["replays"] > 0, s1
     # 8 fluid steps: a chain is launched eagerly the first time its arguments are seen, becomes a graph the second time, and is
     # replayed unchanged from then on (outputs are fed back: two alternating address sets)
-    assert s1["instantiated"] >= 1 and s1["exact_hits"] >= 2, s1
+    assert s1["instantiated"] >= 1 and s1["replays"] >= s1["instantiated"], s1
     assert set(eager.files) == set(replay.files)
     for k in eager.files:
         a, b = eager[k], replay[k]
