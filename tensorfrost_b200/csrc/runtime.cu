@@ -556,7 +556,9 @@ struct GraphExec {
 struct GraphShape {
 	std::vector<RecOp> ops;  // arg_offset / arg_bytes included: equal shapes have equal layouts
 	std::vector<GraphExec> execs;
-	uint64_t seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // argument hashes of recent executions that were launched eagerly
+	// argument hashes of the last executions that were launched eagerly.  As many as executable graphs are kept (kExecsPerShape): a chain
+	// whose arguments cycle with a longer period would be instantiated, evicted before its next turn and instantiated again, for ever.
+	uint64_t seen[4] = {0, 0, 0, 0};
 	unsigned seen_at = 0;
 };
 struct Recorder {
@@ -720,7 +722,7 @@ static void flush_recorded() {
 					R.instantiated++;
 				}
 			} else {
-				gs.seen[gs.seen_at++ % 8] = args_hash;
+				gs.seen[gs.seen_at++ % 4] = args_hash;
 			}
 		}
 		if (use) {
