@@ -374,6 +374,18 @@ def bench_main(args):
         driver_calls = tf.cuda_pool_driver_calls() - driver_calls0
         graph = tf.cuda_graph_stats() if hasattr(tf, "cuda_graph_stats") else None
         loss = tr.step(read_loss=True)
+        # end to end: the same iterations through the public API with HOST data every step - the batch indices and the step's scalars go
+        # up (pageable numpy arrays), the exchanged [gradients, loss] vector comes back and the loss is read on the host (which also
+        # synchronises every iteration); wall clock between device syncs, max over ranks
+        e2e_steps = max(3, args.steps // 2)
+        tf.cuda_synchronize()
+        if dist is not None:
+            dist.barrier()
+        t_e2e = time.perf_counter()
+        for _ in range(e2e_steps):
+            loss = tr.step(read_loss=True)
+        tf.cuda_synchronize()
+        e2e_s = time.perf_counter() - t_e2e
         # replicated state must be bit-identical on every rank (the optimizer step is replicated, nothing is broadcast)
         digest = None
         if not args.nca_mono:
@@ -421,10 +433,11 @@ def bench_main(args):
         alone = single = None
         if dist is not None:
             every = [None] * world
-            dist.all_gather_object(every, (ms, digest))
+            dist.all_gather_object(every, (ms, digest, e2e_s))
             per_rank_ms = [e[0] / args.steps for e in every]
             digests = [e[1] for e in every]
             ms = max(e[0] for e in every)
+            e2e_s = max(e[2] for e in every)
             if not getattr(args, "no_single", False):
                 # references for the scaling numbers, on rank 0's GPU while the peers idle at the barrier below:
                 if rank == 0:
@@ -465,6 +478,9 @@ def bench_main(args):
             "gpu_launches": int(launches), "loss_after": loss, "build_seconds": build_s, "clocks": clocks,
             "host_issue_ms_per_step": host_issue_ms / args.steps, "device_alloc_calls_per_step": driver_calls / args.steps, "graph": graph,
             "host_cores": os.cpu_count(),
+            "e2e": {"value": args.nca_batch * e2e_steps / e2e_s, "unit": "samples/s", "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps,
+                    "h2d_bytes_per_step": world * (4 * (args.nca_batch // world) + 8), "d2h_bytes_per_step": world * 4 * 7821,
+                    "path": "NcaTrainer.step(read_loss=True): numpy batch ids + scalars in, exchanged gradient vector + loss out, every iteration"},
             "verify": {"ok": bool(np.isfinite(loss)) and len(set(digests)) == 1, "loss_finite": bool(np.isfinite(loss)),
                        "parameters_bit_identical_across_ranks": len(set(digests)) == 1, "parity": "tests/test_nca_gpu.py (split and mono step vs reference golden)"},
         }
