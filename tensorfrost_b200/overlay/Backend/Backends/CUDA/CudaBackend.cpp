@@ -117,6 +117,16 @@ void TFCudaBuffer::GetDataAtOffset(size_t offset, size_t count, uint32_t* data) 
 // Active on the CUDA backend (and, for the CPU tests of this very function, on any backend when TFCUDA_HOST_CACHE=1).
 namespace {
 
+// single-quote a path for the shell command below (the cache directory comes from the environment)
+std::string ShellQuote(const std::string& s) {
+	std::string out = "'";
+	for (char c : s) {
+		if (c == '\'') out += "'\\''";
+		else out += c;
+	}
+	return out + "'";
+}
+
 uint64_t Fnv1a(const std::string& s, uint64_t h) {
 	for (unsigned char c : s) {
 		h ^= c;
@@ -147,7 +157,7 @@ bool CudaHostProgramCache(const std::string& code, const char* dll_name, size_t 
 			if (!out) throw std::runtime_error("CUDA backend: cannot write the generated host program to " + src);
 			out << code;
 		}
-		const std::string cmd = "g++ " + flags + " -w -shared -fPIC " + src + " -o " + tmp_so + " 2>&1";
+		const std::string cmd = "g++ " + flags + " -w -shared -fPIC " + ShellQuote(src) + " -o " + ShellQuote(tmp_so) + " 2>&1";
 		std::string output;
 		FILE* pipe = popen(cmd.c_str(), "r");
 		if (!pipe) throw std::runtime_error("CUDA backend: popen(g++) failed");
