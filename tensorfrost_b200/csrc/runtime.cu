@@ -1255,6 +1255,12 @@ int tfcuda_launch(size_t kernel_id, const uint64_t* mem, size_t n_mem, const uin
 		return 1;
 	}
 	if (work_group_count == 0) return 0;
+	// block ids are `int` in the generated code (CPP.cpp:503-515) and emitted kernels state `block_id >= 0` to the compiler (prelude.cuh)
+	if ((n_var ? (uint64_t)vars[n_var - 1] : 0) + (uint64_t)work_group_count > 0x7fffffffull) {
+		set_error("tfcuda_launch: kernel " + std::to_string(kernel_id) + ": " + std::to_string(work_group_count) +
+		          " blocks exceed the 2^31-1 block ids a generated kernel can address");
+		return 1;
+	}
 	// argument block = { uint* mem[n_mem]; uint var[n_var]; } passed by value as the single kernel parameter
 	alignas(8) unsigned char block[4096 + 8];
 	size_t bytes = n_mem * 8 + n_var * 4;

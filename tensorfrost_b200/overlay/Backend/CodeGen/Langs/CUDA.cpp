@@ -16,6 +16,7 @@
 //     uint* <name>_mem = tf_a.mem[i]; ...            // rw bindings first, then ro (KernelGen.h:36-45)
 //     <type> var_<name> = as<type>(tf_a.var[i]); ... // host scalars, declaration order of kernel->variables
 //     int block_id = blockIdx.x + var__kernel_block_offset;      // 1-D grid (CPP.cpp:503-515)
+//     TF_ASSUME(block_id >= 0);                                  // range fact for the compiler (prelude.cuh)
 //     int block_thread_id{0,1,2} = threadIdx.{x,y,z};            // 0 = innermost
 //     <body>
 //   }
@@ -188,6 +189,10 @@ void GenerateCUDAKernel(Program* program, Kernel* kernel) {
 		if (atoi(pdl) != 0) main_code += "  tf_pdl_prologue();\n";  // experimental: programmatic dependent launch (prelude.cuh)
 	}
 	main_code += "  int block_id = (int)(blockIdx.x + var__kernel_block_offset);\n";
+	// a fact the compiler cannot derive (prelude.cuh): lets it drop the `>= 0` half of index clamps and bounds tests.
+	// TFCUDA_ASSUME=0 (debugging aid) leaves it out.
+	static const bool assume_env = !(getenv("TFCUDA_ASSUME") && atoi(getenv("TFCUDA_ASSUME")) == 0);
+	if (assume_env) main_code += "  TF_ASSUME(block_id >= 0);\n";
 	main_code += "  int block_thread_id0 = (int)threadIdx.x;\n";
 	main_code += "  int block_thread_id1 = (int)threadIdx.y;\n";
 	main_code += "  int block_thread_id2 = (int)threadIdx.z;\n";
