@@ -180,7 +180,16 @@ TF_DEV void tf_atomic_add(uint* mem, int a, int v) {
 #else
 TF_DEV void tf_atomic_add(uint* mem, int a, uint v) { atomicAdd(mem + a, v); }
 TF_DEV void tf_atomic_add(uint* mem, int a, int v) { atomicAdd((int*)mem + a, v); }
-TF_DEV void tf_atomic_add(uint* mem, int a, float v) { atomicAdd((float*)mem + a, v); }
+// A float add of exactly zero is skipped: it cannot change the sum (at most the sign of a zero), and the reference's autodiff produces
+// such adds in bulk - the gradient of a concatenation scatters `in_this_half ? g : 0.f` into BOTH halves, with the index of the wrong half
+// clamped to one edge element, so a third of NCA's split kernel's atomics were zeros queueing on the same few addresses.  NaN is not
+// skipped (NaN != 0).  -DTF_ATOMIC_ADD_ZERO=1 restores the unconditional add.
+#ifndef TF_ATOMIC_ADD_ZERO
+#define TF_ATOMIC_ADD_ZERO 0
+#endif
+TF_DEV void tf_atomic_add(uint* mem, int a, float v) {
+	if (TF_ATOMIC_ADD_ZERO || v != 0.0f) atomicAdd((float*)mem + a, v);
+}
 #endif
 TF_DEV uint tf_atomic_add_prev(uint* mem, int a, uint v) { return atomicAdd(mem + a, v); }
 TF_DEV int tf_atomic_add_prev(uint* mem, int a, int v) { return atomicAdd((int*)mem + a, v); }

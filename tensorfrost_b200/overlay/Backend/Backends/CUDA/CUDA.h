@@ -9,6 +9,7 @@
 // mirroring what Backends/CPU/{Memory.h,KernelManager.h} and Backends/OpenGL/{Memory.h,KernelManager.h} do.
 #pragma once
 
+#include <array>
 #include <string>
 #include <vector>
 
@@ -58,6 +59,8 @@ void InstallCudaLibraryLowerings();                     // replaces entries of i
 bool CudaLibraryWantsReduction(Node* node);             // consulted by IR::OptimizeReductions (Steps/Optimization.cpp:471) before it stages a reduction
 std::vector<Tensor*> CudaLibrarySort(const Tensor* keys, const Tensor* values, int max_bits);
 bool IsCudaLibraryKernel(Kernel* kernel);
+// threads per block an emitted kernel is launched with: the IR's group_size, except for coarsened kernels (CodeGen/Langs/CUDA.cpp)
+std::array<int, 3> CudaLaunchBlock(const Kernel* kernel);
 void RegisterCudaLibraryKernel(Kernel* kernel);
 const CudaLibraryCall* FindCudaLibraryCall(size_t kernel_id);
 void DispatchCudaLibraryCall(const CudaLibraryCall& call, const TFDispatchInfo& info);

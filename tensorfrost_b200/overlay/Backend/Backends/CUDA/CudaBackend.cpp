@@ -193,9 +193,8 @@ void CudaKernelManager::CompileProgram(Program* program) {
 		s.kernel_id = kernel.kernel_id_;
 		s.entry = kernel.kernel_name_.c_str();
 		s.source = kernel.full_generated_code_.c_str();
-		vector<int> group = kernel.root->group_size;
-		while (group.size() < 3) group.push_back(1);
-		for (int d = 0; d < 3; d++) s.group[d] = (unsigned)group[d];
+		const std::array<int, 3> block = CudaLaunchBlock(&kernel);  // != kernel.root->group_size for coarsened kernels
+		for (int d = 0; d < 3; d++) s.group[d] = (unsigned)block[d];
 		s.n_mem = (unsigned)kernel.GetMemoryBindings().size();
 		s.n_var = (unsigned)kernel.var_names.size();
 		s.library_op = FindCudaLibraryCall(kernel.kernel_id_) != nullptr ? 1 : 0;  // no source: dispatched by DispatchCudaLibraryCall

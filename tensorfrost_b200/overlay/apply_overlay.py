@@ -122,11 +122,11 @@ def main():
 
     # 4c. default thread-block shapes for CUDA (Steps/GraphOps.cpp:1143-1166)
     p = Patch(tf / "Compiler" / "Steps" / "GraphOps.cpp")
-    p.insert_before("Tensor* IR::LinearBlockModeIndices(", "vector<int> CudaDefaultGroupSize(int dims, const vector<int>& const_shape);  // Backend/CodeGen/Langs/CUDA.cpp\n\n")
+    p.insert_before("Tensor* IR::LinearBlockModeIndices(", "vector<int> CudaDefaultGroupSize(int dims, const vector<int>& const_shape, Node* kernel_node);  // Backend/CodeGen/Langs/CUDA.cpp\n\n")
     p.insert_before("\t\t\t//if the dimensions are known, then use the minimum of the group size and the shape",
                     "\t\t\t{\n\t\t\t\tvector<int> const_shape;\n"
                     "\t\t\t\tfor (int i = 0; i < dims; i++) const_shape.push_back(kernel_shape[i]->TryGetConstant());\n"
-                    "\t\t\t\tvector<int> cuda_group = CudaDefaultGroupSize(dims, const_shape);\n"
+                    "\t\t\t\tvector<int> cuda_group = CudaDefaultGroupSize(dims, const_shape, kernel_);\n"
                     "\t\t\t\tif (!cuda_group.empty()) kernel_->group_size = cuda_group;\n\t\t\t}\n")
     p.save()
 

@@ -55,6 +55,13 @@ def from_words(words, shape, type_id):
     return words
 
 
+def coarsened(kernels):
+    """[kernels whose threads carry several lanes, of which with a lane-by-lane path for blocks on the edge of the dispatch, kernels]"""
+    texts = [k[0][1] + k[0][2] for k in kernels]
+    lanes = [t for t in texts if "lanes per thread" in t]
+    return np.array([len(lanes), sum("tf_lane" in t for t in lanes), len(texts)], np.int64)
+
+
 def kernel_units(kernels, host_code):
     """C++ text of the kernels translation unit: shim + prelude + emitted kernels + one serial launcher per kernel."""
     groups = {}
@@ -78,6 +85,9 @@ def kernel_units(kernels, host_code):
         gx, gy, gz = groups.get(kid, (None, None, None))
         if gx is None:
             continue  # never dispatched by this program
+        lb = re.search(r"// tfcuda_block: (\d+) (\d+) (\d+)", src)
+        if lb:  # the block the kernel is LAUNCHED with (smaller than the IR's for coarsened kernels: each thread carries several lanes)
+            gx, gy, gz = (int(x) for x in lb.groups())
         text.append(src)
         fill_mem = f"for (size_t i = 0; i < {n_mem}; i++) a.mem[i] = mem[i];" if n_mem else ""
         if needs_barrier:
@@ -284,6 +294,7 @@ def main():
                 kernels = tf.get_all_generated_kernels()[seen:]
                 seen += len(kernels)
                 lib = build(fluid.compiled_code(), kernels, "fluid")
+                result[f"{spec}/coarsened"] = coarsened(kernels)
 
                 def call(*state):
                     arrays = [t.numpy if isinstance(t, HostTensor) else t for t in state]
@@ -324,6 +335,7 @@ def main():
                 ids, fire, lr = np.asarray(g["ids"], np.int32), np.array([float(nca.CELL_FIRE_RATE)], np.float32), np.array([float(g["lr"])], np.float32)
                 print(f"[run_sim] nca: grad program {len(kernels)} kernels, apply program {len(apply_kernels)} kernels", file=sys.stderr, flush=True)
                 grad_lib, apply_lib = build(program.compiled_code(), kernels, "nca_grad"), build(apply_program.compiled_code(), apply_kernels, "nca_apply")
+                result[f"{spec}/coarsened"] = coarsened(kernels)
                 losses = []
                 first = None
                 for _ in range(len(g["split_losses"])):  # NcaTrainer.step: grad program -> (exchange) -> apply program
@@ -353,6 +365,7 @@ def main():
             n_out = len(re.findall(r"\bout\[\d+\]\s*=", program.compiled_code()))
             print(f"[run_sim] {name}: {len(kernels)} kernels, {n_out} outputs", file=sys.stderr, flush=True)
             outs = run(build(program.compiled_code(), kernels, name), inputs, n_out, name)
+            result[f"{spec}/coarsened"] = coarsened(kernels)
             for k, o in enumerate(outs):
                 result[f"{spec}/{k}"] = o
     finally:

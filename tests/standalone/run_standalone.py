@@ -29,7 +29,7 @@ NP_OF = {0: np.float32, 1: np.uint32, 2: np.int32, 3: np.uint32}
 
 def kernel_sources(kernels, host_code, abi):
     """TFCudaKernelSource records for every emitted kernel the host program dispatches (group sizes are baked into the kernel; the host
-    text carries them as the last argument of tf.dispatch: CPP.cpp:622-629)."""
+    text carries the IR's as the last argument of tf.dispatch, CPP.cpp:622-629, the kernel text the launched one as `// tfcuda_block:`)."""
     groups = {}
     for line in host_code.splitlines():
         m = re.search(r"tf\.dispatch\((\d+),.*\{([^{}]*)\}\);\s*$", line)
@@ -52,8 +52,12 @@ def kernel_sources(kernels, host_code, abi):
         entry, text = f"kernel_{kid}".encode(), src.encode()
         keep += [entry, text]
         rec.entry, rec.source = entry, text
+        # threads per block: the emitter states them (a coarsened kernel is launched with a smaller block than the one the host
+        # program's block count was computed for); the tf.dispatch text is the IR's block
+        lb = re.search(r"// tfcuda_block: (\d+) (\d+) (\d+)", src)
+        block = [int(x) for x in lb.groups()] if lb else groups[kid]
         for d in range(3):
-            rec.group[d] = groups[kid][d]
+            rec.group[d] = block[d]
         rec.n_mem = int(nm.group(1)) if nm else 0
         rec.n_var = int(nv.group(1))
         rec.library_op = 0
