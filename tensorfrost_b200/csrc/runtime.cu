@@ -576,7 +576,9 @@ struct Recorder {
 };
 static Recorder g_rec;
 static const size_t kMinGraphOps = 4;
-static const uint64_t kSmallKernelThreads = 1ull << 21;  // below ~2 M threads a kernel on 148 SMs is over in a few microseconds
+// below ~1 M threads a kernel on 148 SMs is over in a few microseconds.  (Kernels the emitter coarsens - 4 elements per thread, only
+// above 2^22 elements - keep at least 2^20 threads, so they count as long kernels here exactly as before they were coarsened.)
+static const uint64_t kSmallKernelThreads = 1ull << 20;
 static const size_t kExecsPerShape = 4;
 static const size_t kMaxShapes = 256;
 

@@ -94,6 +94,7 @@ struct CudaCoarsening {
 	int dim = 0;      // group dimension the lanes run along
 	int factor = 1;   // lanes per CUDA thread
 	bool exact = false;  // every constant extent is a multiple of the virtual block: the dispatch guard is always true
+	vector<int> group;   // the enlarged block handed to the IR (checked again at emission: the table is keyed by node address)
 };
 static unordered_map<const Node*, CudaCoarsening> g_coarsened;   // kernel node -> decision taken when its default block was chosen
 static unordered_map<size_t, array<int, 3>> g_launch_block;      // kernel id -> threads per block the kernel is launched with
@@ -187,6 +188,7 @@ vector<int> CudaDefaultGroupSize(int dims, const vector<int>& const_shape, Node*
 	c.factor = factor;
 	c.exact = true;
 	for (int d = 0; d < (int)group.size(); d++) c.exact = c.exact && (const_shape[d] % group[d] == 0);
+	c.group = group;
 	g_coarsened[kernel_node] = c;
 	return group;
 }
@@ -445,7 +447,8 @@ void GenerateCUDAKernel(Program* program, Kernel* kernel) {
 	int coarsened_dim = -1;
 	{
 		auto it = g_coarsened.find(kernel->root);
-		if (it != g_coarsened.end()) {
+		const bool group_memory = !GetGroupBufferDeclarations(kernel, CudaSharedDeclaration).empty();
+		if (it != g_coarsened.end() && it->second.group == kernel->root->group_size && !group_memory) {
 			const CudaCoarsening c = it->second;
 			if (c.dim < 3 && c.factor > 1 && group[c.dim] % c.factor == 0) {
 				const int real_extent = group[c.dim] / c.factor;

@@ -89,3 +89,21 @@ for k in tf.get_all_generated_kernels():
     for _, kid, flag, block, ir_block, n_lines in rows:
         if flag == "0":
             assert (block + ",1,1").split(",")[:len(ir_block.split(","))] == ir_block.split(","), (kid, block, ir_block)
+
+
+def test_nca_training_step_with_lanes_reproduces_the_reference(tmp_path):
+    """The NCA grad program (float atomics, random masks, 3 CA steps + autodiff) with 29 of its 83 kernels carrying lanes - six of them with
+    the lane-by-lane edge path - against the reference's own gradients, loss and 3-iteration loss sequence (tests/golden/nca_step.npz)."""
+    _ready()
+    out, proc = _sim(tmp_path, "nca", {"TFCUDA_COARSEN_MIN_ELEMENTS": "1"}, ["nca"])
+    _, err = proc.communicate(timeout=1200)
+    assert proc.returncode == 0, err[-3000:]
+    got = np.load(out)
+    lanes, with_edge_path, kernels = got["nca/coarsened"]
+    assert lanes >= 20 and with_edge_path >= 1, (lanes, with_edge_path, kernels)
+    nca = np.load(os.path.join(HERE, "golden", "nca_step.npz"))
+    flat = got["nca/2"]
+    scale = np.abs(nca["flat0"][:-1]).max()
+    assert np.abs(flat[:-1].astype(np.float64) - nca["flat0"][:-1]).max() <= 1e-5 * scale
+    assert abs(float(flat[-1]) - float(nca["split_losses"][0])) <= 1e-6
+    np.testing.assert_allclose(got["nca/losses"], nca["split_losses"], rtol=1e-5)
