@@ -70,9 +70,16 @@ def gloo_exchange(flat, world):
     return tf.tensor((t / world).numpy())
 
 mode = {mode!r}
+# The ORACLE compiles every program from the fixed path /tmp/generated_lib_<id>.cpp (Backends/CPU/KernelCompiler.cpp:93-113): two ranks
+# tracing at the same instant overwrite each other's source (the race the CUDA backend's host-program cache removes, DESIGN.md 12).
+# On the unmodified reference the ranks therefore take turns: tf.compile runs g++ inside the constructor, before any collective.
+import fcntl
+lock = open(os.path.join(os.path.dirname({out!r}), "compile.lock"), "w")
+fcntl.flock(lock, fcntl.LOCK_EX)
 # "same": both ranks see the SAME data and RNG stream, so the averaged gradient equals the single-rank one.
 tr = nca_dp.NcaTrainer(tf, global_batch=4 * world if mode == "same" else 4, grid=24, pool_size=16 * world if mode == "same" else 16,
                        train_steps=2, rank=rank, world=world, exchange=gloo_exchange, rank_seed_offset=0 if mode == "same" else 1000003)
+fcntl.flock(lock, fcntl.LOCK_UN)
 ids = np.array([3, 7, 1, 12], np.int32)[: tr.batch]
 losses = [tr.step(batch_ids=ids if mode == "same" else None, lr=0.002, read_loss=True) for _ in range(2)]
 params = tr.parameters_numpy()
