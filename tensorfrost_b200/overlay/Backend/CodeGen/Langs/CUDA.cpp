@@ -76,11 +76,6 @@ class CUDAGenerator : public CodeGenerator {
 
 }  // namespace
 
-// Default thread-block shape for kernels the user did not size (consulted by IR::LinearBlockModeIndices, Steps/GraphOps.cpp:1143-1166,
-// which otherwise picks 256 / 16x16 / 8x8x8).  On a GPU the innermost kernel dimension is the contiguous one in memory, so a warp
-// should span 32 consecutive innermost indices (one 128-byte line per row) instead of 16 or 8; the remaining threads go to the
-// outer dimensions.  const_shape[i] > 0 where the extent is a compile-time constant (blocks never exceed it).  Returns {} for
-// other kernel languages.
 // ---- thread coarsening (SURVEY.md 2.2 / VERDICT r1 "emitter that moves more than 4 B per thread") ---------------------------------
 // A streaming kernel with one element per thread keeps one 4-byte load per input in flight per thread: ~8 KB per SM at full occupancy where
 // Little's law asks for ~35 KB at HBM3e rate and latency (measured round 2: NCA's bias + LeakyReLU kernel 2.6 TB/s, fluid's Jacobi and
@@ -126,6 +121,11 @@ static bool CudaKernelIsCoarsenable(Node* kernel_node) {
 	return nodes > 0 && nodes <= 200 && memory_ops <= 14;
 }
 
+// Default thread-block shape for kernels the user did not size (consulted by IR::LinearBlockModeIndices, Steps/GraphOps.cpp:1143-1166,
+// which otherwise picks 256 / 16x16 / 8x8x8).  On a GPU the innermost kernel dimension is the contiguous one in memory, so a warp
+// should span 32 consecutive innermost indices (one 128-byte line per row) instead of 16 or 8; the remaining threads go to the
+// outer dimensions.  const_shape[i] > 0 where the extent is a compile-time constant (blocks never exceed it).  Returns {} when
+// the reference's own defaults are asked for.
 static vector<int> CudaBaseGroupSize(int dims, const vector<int>& const_shape) {
 	if (const char* v = getenv("TFCUDA_DEFAULT_GROUP")) {
 		if (atoi(v) == 0) return {};  // debugging aid: the reference's own 256 / 16x16 / 8x8x8 defaults
@@ -154,6 +154,8 @@ static vector<int> CudaBaseGroupSize(int dims, const vector<int>& const_shape) {
 	return group;
 }
 
+// The block IR::LinearBlockModeIndices uses for a kernel the user did not size: the shape above, enlarged along one dimension when the
+// kernel is going to be coarsened.  Returns {} for other kernel languages (the reference's defaults apply).
 vector<int> CudaDefaultGroupSize(int dims, const vector<int>& const_shape, Node* kernel_node) {
 	if (current_kernel_lang != CodeGenLang::CUDA) return {};
 	if (kernel_node != nullptr) g_coarsened.erase(kernel_node);  // a recycled node address must not inherit an old decision
