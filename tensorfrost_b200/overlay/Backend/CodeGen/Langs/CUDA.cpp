@@ -103,12 +103,13 @@ static int CudaCoarsenFactor() {
 	return factor;
 }
 
-// straight-line body, few memory operations, nothing that ties the block shape to the program (barriers, group memory, thread ids)
+// straight-line body (loops every lane runs in step are allowed: the emitter checks their headers), few memory operations, nothing that
+// ties the block shape to the program (barriers, group memory, thread ids)
 static bool CudaKernelIsCoarsenable(Node* kernel_node) {
 	int nodes = 0, memory_ops = 0;
 	for (auto node = NodeIterator(kernel_node); !node.end(); node.next()) {
 		const Operation* op = node->op;
-		if (op->HasAllTypes(OpProp::HasChildren) || op->class_ == OpClass::Keyword || op->HasAllTypes(OpProp::LocalMemory) ||
+		if ((op->HasAllTypes(OpProp::HasChildren) && op->name_ != "loop") || op->class_ == OpClass::Keyword || op->HasAllTypes(OpProp::LocalMemory) ||
 		    node->flags.has(NodeProp::LocalMemoryOp) || op->name_ == "group_barrier" || op->name_ == "block_thread_id") {
 			if (getenv("TFCUDA_COARSEN_DEBUG")) fprintf(stderr, "[tfcuda coarsen] refused: %s\n", op->name_.c_str());
 			return false;
@@ -118,7 +119,9 @@ static bool CudaKernelIsCoarsenable(Node* kernel_node) {
 	}
 	static const bool debug = getenv("TFCUDA_COARSEN_DEBUG") != nullptr;
 	if (debug) fprintf(stderr, "[tfcuda coarsen] %s: %d nodes, %d memory ops\n", kernel_node->debug_name.c_str(), nodes, memory_ops);
-	return nodes > 0 && nodes <= 200 && memory_ops <= 14;
+	static const int max_memory_ops = getenv("TFCUDA_COARSEN_MAX_MEMOPS") ? atoi(getenv("TFCUDA_COARSEN_MAX_MEMOPS")) : 28;  // tuning aid
+	static const int max_nodes = getenv("TFCUDA_COARSEN_MAX_NODES") ? atoi(getenv("TFCUDA_COARSEN_MAX_NODES")) : 240;
+	return nodes > 0 && nodes <= max_nodes && memory_ops <= max_memory_ops;
 }
 
 // Default thread-block shape for kernels the user did not size (consulted by IR::LinearBlockModeIndices, Steps/GraphOps.cpp:1143-1166,
@@ -324,13 +327,22 @@ string CoarsenBody(const string& body, const CudaCoarsening& c, int real_extent)
 		if (!IsPlainStatement(t)) return "";
 		prologue.push_back(t);
 	}
+	// payload lines are statements (replicated per lane) or the structure of a loop every lane runs in step: `for (...)` with a header
+	// that names nothing lane-dependent (the 9-tap loops of a filter), and its braces - emitted once around the lanes' statements
+	vector<bool> shared;
+	int depth = 0;
 	for (int i = guard + 3; i < last; i++) {
 		const string t = Trimmed(lines[i]);
 		if (t.empty()) continue;
-		if (!IsPlainStatement(t)) return "";
+		const bool brace = t == "{" || t == "}";
+		const bool loop_header = t.rfind("for (", 0) == 0 && t.back() == ')';
+		if (!brace && !loop_header && !IsPlainStatement(t)) return "";
+		if (t == "{") depth++;
+		if (t == "}" && --depth < 0) return "";
 		payload.push_back(t);
+		shared.push_back(brace || loop_header);
 	}
-	if (payload.empty() || payload.size() > 128) return "";
+	if (depth != 0 || payload.empty() || payload.size() > 128) return "";
 	// names that become per-lane: everything the body declares + the thread id the lanes run along
 	unordered_set<string> names = {tid_name};
 	unordered_set<string> all_tokens;
@@ -351,6 +363,11 @@ string CoarsenBody(const string& body, const CudaCoarsening& c, int real_extent)
 			}
 		}
 	}
+	// a loop header must read the same for every lane
+	for (size_t i = 0; i < payload.size(); i++) {
+		if (!shared[i] || payload[i] == "{" || payload[i] == "}") continue;
+		if (RenameIdentifiers(payload[i], names, "_") != payload[i]) return "";
+	}
 	auto suffix = [](int lane) { return "_L" + to_string(lane); };
 	for (const string& name : names)
 		for (int lane = 0; lane < c.factor; lane++)
@@ -364,8 +381,13 @@ string CoarsenBody(const string& body, const CudaCoarsening& c, int real_extent)
 	out += "if (";
 	for (int lane = 0; lane < c.factor; lane++) out += string(lane ? " && " : "") + "is_inside_dispatch" + suffix(lane);
 	out += ")\n{\n";
-	for (const string& t : payload)
-		for (int lane = 0; lane < c.factor; lane++) out += "  " + RenameIdentifiers(t, names, suffix(lane)) + "\n";
+	for (size_t i = 0; i < payload.size(); i++) {
+		if (shared[i]) {
+			out += "  " + payload[i] + "\n";
+			continue;
+		}
+		for (int lane = 0; lane < c.factor; lane++) out += "  " + RenameIdentifiers(payload[i], names, suffix(lane)) + "\n";
+	}
 	out += "}\n";
 	if (!c.exact) {
 		// a block that crosses the edge of the dispatch: lane by lane through the untouched body

@@ -58,8 +58,8 @@ def test_lane_code_is_bit_identical_to_one_element_per_thread(tmp_path):
 
 
 def test_which_kernels_of_the_benchmark_programs_get_lanes(tmp_path):
-    """At the benchmark size (2048 x 2048) the five full-resolution stencil kernels of the fluid step are coarsened, the multigrid
-    sweeps on the 512 / 1024 grids (launch-bound, too few blocks) and the two long kernels (advection, final projection) are not; the
+    """At the benchmark size (2048 x 2048) the six full-resolution straight-line kernels of the fluid step are coarsened, the multigrid
+    sweeps on the 512 / 1024 grids (launch-bound, too few blocks) and the advection kernel (84 data-dependent gathers) are not; the
     kernel text states the block it must be launched with, which differs from the block of the host program's dispatch."""
     _ready()
     script = r"""
@@ -83,7 +83,7 @@ for k in tf.get_all_generated_kernels():
     rows = [l.split() for l in r.stdout.splitlines() if l.startswith("KERNEL")]
     assert len(rows) == 15
     lanes = [row for row in rows if row[2] == "1"]
-    assert len(lanes) == 5, rows
+    assert len(lanes) == 6, rows
     for _, kid, _, block, ir_block, _ in lanes:
         assert block == "32,8,1" and ir_block == "32,32", (kid, block, ir_block)
     for _, kid, flag, block, ir_block, n_lines in rows:
@@ -92,15 +92,16 @@ for k in tf.get_all_generated_kernels():
 
 
 def test_nca_training_step_with_lanes_reproduces_the_reference(tmp_path):
-    """The NCA grad program (float atomics, random masks, 3 CA steps + autodiff) with 29 of its 83 kernels carrying lanes - six of them with
-    the lane-by-lane edge path - against the reference's own gradients, loss and 3-iteration loss sequence (tests/golden/nca_step.npz)."""
+    """The NCA grad program (float atomics, random masks, 9-tap filter loops, 3 CA steps + autodiff) with 62 of its 83 kernels carrying
+    lanes - 21 of them with the lane-by-lane edge path, the filter kernels with their tap loop shared by the lanes - against the
+    reference's own gradients, loss and 3-iteration loss sequence (tests/golden/nca_step.npz)."""
     _ready()
     out, proc = _sim(tmp_path, "nca", {"TFCUDA_COARSEN_MIN_ELEMENTS": "1"}, ["nca"])
     _, err = proc.communicate(timeout=1200)
     assert proc.returncode == 0, err[-3000:]
     got = np.load(out)
     lanes, with_edge_path, kernels = got["nca/coarsened"]
-    assert lanes >= 20 and with_edge_path >= 1, (lanes, with_edge_path, kernels)
+    assert lanes >= 40 and with_edge_path >= 1, (lanes, with_edge_path, kernels)
     nca = np.load(os.path.join(HERE, "golden", "nca_step.npz"))
     flat = got["nca/2"]
     scale = np.abs(nca["flat0"][:-1]).max()
