@@ -158,13 +158,17 @@ uint64_t tfcuda_pool_driver_calls(void);
  *   extern "C" __global__ void kernel_<id>(const __grid_constant__ kernel_<id>_args a);
  * n_var counts the trailing _kernel_block_offset word.  Grid = work_group_count x 1 x 1,
  * block = group[0] x group[1] x group[2] (group sizes are baked into the kernel:
- * kernel->root->group_size, CPP.cpp:622-629).
+ * kernel->root->group_size, CPP.cpp:622-629).  A kernel the emitter coarsened (several "lanes" per
+ * thread) is launched with a SMALLER block than the group the host program's block count was
+ * computed for; its text states the launch block as a comment `// tfcuda_block: x y z`, and that
+ * is what `group` below must carry.  At most 2^31-1 block ids per dispatch (they are `int` in the
+ * generated code, and emitted kernels tell the compiler so).
  * ------------------------------------------------------------------------------------------ */
 typedef struct TFCudaKernelSource {
 	size_t kernel_id;     /* TFDispatchInfo.kernel_id this source serves */
 	const char* entry;    /* extern "C" symbol, e.g. "kernel_12" */
 	const char* source;   /* CUDA C++ text of this kernel WITHOUT the prelude */
-	unsigned group[3];    /* threads per block, innermost first */
+	unsigned group[3];    /* threads per block the kernel is LAUNCHED with, innermost first */
 	unsigned n_mem;       /* number of buffer bindings */
 	unsigned n_var;       /* number of 32-bit scalar words incl. _kernel_block_offset */
 	unsigned library_op;  /* 0 = emitted source; otherwise a TFCUDA_LIB_* id (source may be "") */

@@ -77,9 +77,14 @@ for k in tf.get_all_generated_kernels():
     block = re.search(r"// tfcuda_block: (\d+) (\d+) (\d+)", text).groups()
     ir_block = re.search(r"tf\.dispatch\(%%d,.*\{([^{}]*)\}\);" %% kid, host).group(1).replace(" ", "")
     print("KERNEL", kid, int("lanes per thread" in text), ",".join(block), ir_block, len(text.splitlines()))
+from tensorfrost_b200 import abi
+unit = "\n".join(k[0][1] + k[0][2] for k in tf.get_all_generated_kernels())
+rc = abi.lib().tfcuda_nvrtc_check(unit.encode(), b"")
+print("NVRTC", rc, abi.lib().tfcuda_last_error().decode(errors="replace")[:2000] if rc else "")
 """ % ROOT
     r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
     assert r.returncode == 0, r.stderr[-3000:]
+    assert "NVRTC 0" in r.stdout, r.stdout[-3000:]  # the lane code compiles for sm_100a
     rows = [l.split() for l in r.stdout.splitlines() if l.startswith("KERNEL")]
     assert len(rows) == 15
     lanes = [row for row in rows if row[2] == "1"]
