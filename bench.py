@@ -381,11 +381,23 @@ def verify_fluid(tf, fluid, workloads, args):
             "against": "reference C++/OpenMP backend (oracle/_ref, -O3 -fopenmp, no fast-math), same inputs, this box's host"}
 
 
+def emitter_stats(tf):
+    """How the timed program was emitted: kernels, and how many of them carry several elements ("lanes") per thread."""
+    try:
+        texts = [k[0][1] + k[0][2] for k in tf.get_all_generated_kernels()]
+    except Exception:  # noqa: BLE001
+        return None
+    texts = [t for t in texts if "__global__" in t]
+    return {"kernels": len(texts), "with_lanes": sum("lanes per thread" in t for t in texts),
+            "lanes_per_thread": int(os.environ.get("TFCUDA_COARSEN", "4") or 0), "range_fact": os.environ.get("TFCUDA_ASSUME", "1") != "0"}
+
+
 def bench_fluid(tf, dist, rank, world, args, peaks):
     import numpy as np
     from tensorfrost_b200 import workloads
     n = args.size
     fluid = workloads.load_fluid(tf, n, n)
+    emitter = emitter_stats(tf) if hasattr(tf, "get_all_generated_kernels") else None
     host_inputs = workloads.fluid_inputs(n, n)
     state = [tf.cuda_tensor(a) for a in host_inputs]
     for _ in range(max(args.warmup, 3)):
@@ -476,7 +488,7 @@ def bench_fluid(tf, dist, rank, world, args, peaks):
         except Exception as e:  # noqa: BLE001
             verify = {"ok": None, "skipped": f"{type(e).__name__}: {e}"[:200]}
     return {"value": value, "ms": ms, "launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e, "step_bytes": step_bytes,
-            "counted_bytes": counted_bytes, "graph": graph, "verify": verify,
+            "counted_bytes": counted_bytes, "graph": graph, "verify": verify, "emitter": emitter,
             "records": sorted(records, key=lambda r: -r["total_ms"])[:16]}
 
 
@@ -790,7 +802,7 @@ def nca_single_gpu(args):
         if j is None:
             return {"error": "NCA leg printed no JSON: " + (r.stderr[-300:] or r.stdout[-300:])}
         keep = ("metric", "value", "unit", "n_gpus", "ms_per_step", "scaling", "config", "gpu_launches", "loss_after", "build_seconds", "graph",
-                "host_issue_ms_per_step", "verify")
+                "host_issue_ms_per_step", "verify", "emitter")
         return {k: j[k] for k in keep if k in j}
     except Exception as e:  # noqa: BLE001
         return {"error": f"failed: {e}"}
@@ -828,7 +840,7 @@ def make_line(args, world, res):
         "ms_per_step": res["ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": cfg, "parallelism": "replicas only (single-device program)" if world > 1 else "1 GPU",
         "bytes_per_step_counted_live": res.get("counted_bytes"), "gpu_launches": int(res["launches"]), "clocks": res["clocks"], "roofline": res["roofline"], "e2e": res["e2e"],
-        "graph_replay": res.get("graph"), "verify": res.get("verify"), "top_kernels": res["records"],
+        "graph_replay": res.get("graph"), "verify": res.get("verify"), "emitter": res.get("emitter"), "top_kernels": res["records"],
     }
 
 

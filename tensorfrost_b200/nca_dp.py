@@ -358,6 +358,14 @@ def bench_main(args):
                         rank=rank, world=world, mono=args.nca_mono)
         tr.method = method
         build_s = time.perf_counter() - t0
+        emitter = None
+        try:  # how the per-rank programs were emitted: kernels, and how many carry several elements ("lanes") per thread
+            texts = [k[0][1] + k[0][2] for k in tf.get_all_generated_kernels()]
+            texts = [t for t in texts if "__global__" in t]
+            emitter = {"kernels": len(texts), "with_lanes": sum("lanes per thread" in t for t in texts),
+                       "lanes_per_thread": int(os.environ.get("TFCUDA_COARSEN", "4") or 0)}
+        except Exception:  # noqa: BLE001
+            pass
         # the first ~25 iterations of a fresh process run up to 10 % slower than the steady state (measured at 8 GPUs: 70.0 ms averaged over
         # iterations 6-25, 63.2 ms afterwards; the reference pool above the runtime is still adapting its expiry times): warm up at least 12
         # iterations, the same for the two single-GPU references below, and report the number actually used
@@ -475,7 +483,7 @@ def bench_main(args):
                        "program": "reference single program" if args.nca_mono else "grad program -> allreduce -> apply program",
                        "matmul": {"tf32": "tf.initialize(tf.cuda, '--tf-matmul=tf32'): one tcgen05 kind::tf32 product per matmul (1e-3 class)",
                                   "3xtf32": "backend default: 3xTF32 split products (fp32-accurate)", "fp32": "FFMA kernel"}[matmul]},
-            "gpu_launches": int(launches), "loss_after": loss, "build_seconds": build_s, "clocks": clocks,
+            "gpu_launches": int(launches), "loss_after": loss, "build_seconds": build_s, "emitter": emitter, "clocks": clocks,
             "host_issue_ms_per_step": host_issue_ms / args.steps, "device_alloc_calls_per_step": driver_calls / args.steps, "graph": graph,
             "host_cores": os.cpu_count(),
             "e2e": {"value": args.nca_batch * e2e_steps / e2e_s, "unit": "samples/s", "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps,

@@ -24,8 +24,10 @@ import tensorfrost_b200
 from tensorfrost_b200 import workloads
 tf = tensorfrost_b200.load()
 out = {}
+keep = []  # programs must stay alive: the module's kernel registry holds raw pointers into them (Backend/KernelManager.cpp:4-8)
 for n, m in ((256, 256), (100, 72)):
     fluid = workloads.load_fluid(tf, n, m)
+    keep.append(fluid)
     state = [tf.cuda_tensor(a) for a in workloads.fluid_inputs(n, m)]
     for step in range(6):
         state[4] = tf.cuda_tensor(workloads.fluid_parity_mouse(step, n, m))
