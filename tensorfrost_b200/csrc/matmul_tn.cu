@@ -32,6 +32,14 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) matmul_tn_kernel(const 
 	const long long r_end = min(R, r_begin + rows_per_split);
 	const int tid = threadIdx.x;
 	const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+	// Columns of a thread's register tile.  A thread whose TN columns were contiguous (tx * TN ...) would read shared memory at a stride of
+	// TN words across the lanes of a warp: with TN = 8 four lanes share a bank on every b load (4-way conflict, and the b loads outnumber
+	// the a loads 2:1).  So a TN that is a multiple of 4 is split into groups of 4 columns, group g at g * GROUP_STRIDE + tx * 4: the
+	// lanes of a warp then read consecutive 16-byte words (one conflict-free LDS.128 per group), and global stores of a row of C are
+	// 16 bytes per lane, consecutive across lanes.  Narrow tiles (TN = 2) keep the contiguous layout (8-byte stride: conflict-free).
+	constexpr bool GROUPED = (TN % 4 == 0);
+	constexpr int GROUP_STRIDE = (BN / TN) * 4;
+	auto column = [&](int j) { return GROUPED ? (j / 4) * GROUP_STRIDE + tx * 4 + (j % 4) : tx * TN + j; };
 
 	float acc[TM][TN];
 #pragma unroll
@@ -117,10 +125,18 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) matmul_tn_kernel(const 
 						a[i] = t.x; a[i + 1] = t.y; a[i + 2] = t.z; a[i + 3] = t.w;
 					}
 				}
+				if (GROUPED) {
 #pragma unroll
-				for (int j = 0; j < TN; j += 2) {
-					const float2 t = *reinterpret_cast<const float2*>(&Bs[buf][kk][tx * TN + j]);
-					b[j] = t.x; b[j + 1] = t.y;
+					for (int j = 0; j < TN; j += 4) {
+						const float4 t = *reinterpret_cast<const float4*>(&Bs[buf][kk][(j / 4) * GROUP_STRIDE + tx * 4]);
+						b[j] = t.x; b[j + 1] = t.y; b[j + 2] = t.z; b[j + 3] = t.w;
+					}
+				} else {
+#pragma unroll
+					for (int j = 0; j < TN; j += 2) {
+						const float2 t = *reinterpret_cast<const float2*>(&Bs[buf][kk][tx * TN + j]);
+						b[j] = t.x; b[j + 1] = t.y;
+					}
 				}
 #pragma unroll
 				for (int i = 0; i < TM; i++)
@@ -139,7 +155,7 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) matmul_tn_kernel(const 
 		if (gm >= M) continue;
 #pragma unroll
 		for (int j = 0; j < TN; j++) {
-			const int gn = n0 + tx * TN + j;
+			const int gn = n0 + column(j);
 			if (gn < N) out[(size_t)gm * N + gn] = acc[i][j];
 		}
 	}
@@ -185,8 +201,10 @@ int launch_tn(const float* a, const float* b, float* c, size_t r, size_t m, size
 	tfcuda::State& s = tfcuda::state();
 	const int tiles_m = (int)((m + BM - 1) / BM), tiles_n = (int)((n + BN - 1) / BN);
 	const long tiles = (long)tiles_m * tiles_n;
-	// split the contraction so that ~4 CTAs per SM are in flight; every split is a whole number of stages
-	long splits = std::max<long>(1, std::min<long>(((long)s.sm_count * 4 + tiles - 1) / tiles, (long)((r + 8 * TN_BR - 1) / (8 * TN_BR))));
+	// split the contraction so that ~4 CTAs per SM are in flight - what the register file holds of the 8x8 tiles (128 registers x 128
+	// threads, or 167 x 96 for the 48-row tile), i.e. one wave; every split is a whole number of stages
+	constexpr int ctas_per_sm = 4;
+	long splits = std::max<long>(1, std::min<long>(((long)s.sm_count * ctas_per_sm + tiles - 1) / tiles, (long)((r + 8 * TN_BR - 1) / (8 * TN_BR))));
 	long long rows_per_split = (long long)((r + splits - 1) / splits);
 	rows_per_split = (rows_per_split + TN_BR - 1) / TN_BR * TN_BR;
 	splits = (long)((r + rows_per_split - 1) / rows_per_split);
@@ -242,6 +260,8 @@ extern "C" int tfcuda_matmul_tn(uint64_t a, uint64_t b, uint64_t c, size_t r, si
 	// narrow outputs (e.g. the 12 output channels of NCA's second layer) take a tall tile so that lanes are not wasted on padding
 	if (n <= 16) return launch_tn<128, 16, 8, 2>(pa, pb, pc, r, m, n);
 	if (n <= 32) return launch_tn<128, 32, 8, 4>(pa, pb, pc, r, m, n);
+	// a short M (the 48 input channels of NCA's first layer) takes a 48-row tile: the 64-row tile would spend a quarter of its FFMAs on padding
+	if (m <= 48) return launch_tn<48, 128, 8, 8>(pa, pb, pc, r, m, n);
 	return launch_tn<64, 128, 8, 8>(pa, pb, pc, r, m, n);
 }
 #endif  // TF_HOST_SIM

@@ -155,6 +155,9 @@ int main() {
 	ok &= check_nbody(5000, true);
 	// control: the hardware-validated weight-gradient kernel through the same harness
 	ok &= check_tn<64, 128, 8, 8>(1000, 48, 128, 5);
+	ok &= check_tn<64, 128, 8, 8>(500, 100, 200, 3);   // several tiles in both directions, ragged in both (grouped column layout of the 8-wide tile)
+	ok &= check_tn<48, 128, 8, 8>(1000, 48, 128, 5);   // the 48-row tile NCA's first layer takes (96 threads)
+	ok &= check_tn<48, 128, 8, 8>(333, 37, 130, 4);    // M and N not multiples of 4: scalar loads, two column tiles, ragged tails
 	ok &= check_tn<128, 16, 8, 2>(777, 128, 12, 3);
 	ok &= check_tn<128, 32, 8, 4>(300, 20, 24, 2);
 	// the skinny matmul written without a GPU: every template configuration the dispatcher uses, NCA's four shapes, ragged tails
