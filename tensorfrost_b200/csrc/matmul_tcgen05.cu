@@ -19,6 +19,7 @@
 #include <cuda.h>
 
 #include "tfcuda_internal.h"
+#include "epilogue_store.cuh"
 
 namespace {
 
@@ -250,8 +251,6 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 			tile_coords(tile, g.tiles_m, g.tiles_n, m_blk, n_blk);
 			mbar_wait(tmem_full_bar(acc), acc_phase);
 			tcgen05_fence_after();
-			const int row = m_blk * BLOCK_M + quarter * 32 + lane;
-			float* crow = g.c + (size_t)row * g.n;
 #pragma unroll 1
 			for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
 				uint32_t r[32];
@@ -260,20 +259,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 				if (g.dbg && blockIdx.x == 0 && tile == 0 && c0 == 0 && lane == 0) {
 					for (int i = 0; i < 8; i++) g.dbg[160 + quarter * 8 + i] = r[i];
 				}
-				const int col = n_blk * BLOCK_N + c0;
-				if (row < g.m) {
-					if (col + 32 <= g.n) {
-#pragma unroll
-						for (int j = 0; j < 32; j += 4) {
-							float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-							*reinterpret_cast<float4*>(crow + col + j) = v;
-						}
-					} else {
-#pragma unroll
-						for (int j = 0; j < 32; j++)
-							if (col + j < g.n) crow[col + j] = __uint_as_float(r[j]);
-					}
-				}
+				// octet-transposed store: every store instruction of the warp covers 4 rows x 128 contiguous bytes (epilogue_store.cuh)
+				store_block_32x32(r, g.c, (size_t)g.n, m_blk * BLOCK_M + quarter * 32, n_blk * BLOCK_N + c0, g.m, g.n, lane);
 			}
 			tcgen05_fence_before();
 			__syncwarp();

@@ -21,6 +21,19 @@ static inline float4 make_float4(float x, float y, float z, float w) { return fl
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 #define __align__(n) __attribute__((aligned(n)))
 
+// warp shuffle stand-in for blocks of ONE warp (launch(..., 32, ...)): every lane publishes its value, the block barrier, every lane
+// reads its partner's - all lanes of the warp must call it, as on the device with a full mask
+static unsigned sim_shfl_slot[32];
+static inline unsigned __shfl_xor_sync(unsigned, unsigned v, int lane_mask) {
+	sim_shfl_slot[threadIdx.x] = v;
+	__syncthreads();
+	const unsigned out = sim_shfl_slot[threadIdx.x ^ (unsigned)lane_mask];
+	__syncthreads();
+	return out;
+}
+// the octet-transposed store of the tcgen05 matmul's epilogue (plain CUDA: the part of that kernel that CAN run here)
+#include "epilogue_store.cuh"
+
 // matmul_tn.cu declares fixed-size __shared__ arrays inside its kernel: statics shared by the block's threads (the shim's default)
 #include "matmul_tn.cu"
 
@@ -114,6 +127,29 @@ static bool check_tn(size_t r, size_t m, size_t n, long splits) {
 	return e <= 2e-6;
 }
 
+// store_block_32x32 against the direct store of the layout it receives (lane = row, r[j] = column j): every element inside m x n written
+// with its own value, nothing outside touched (the buffer is NaN-filled with a margin)
+static bool check_epilogue_store(int m, int n, int row0, int col0) {
+	const int ldc = n, pad_rows = 40;
+	std::vector<float> c((size_t)(m + pad_rows) * ldc, std::nanf(""));
+	auto value = [&](int row, int col) { return (float)(row * 1000 + col) + 0.25f; };
+	launch(1, 1, 32, [&]() {
+		const int lane = (int)threadIdx.x;
+		uint32_t r[32];
+		for (int j = 0; j < 32; j++) r[j] = __float_as_uint(value(row0 + lane, col0 + j));
+		store_block_32x32(r, c.data(), (size_t)ldc, row0, col0, m, n, lane);
+	});
+	bool good = true;
+	for (int row = 0; row < m + pad_rows && good; row++)
+		for (int col = 0; col < ldc; col++) {
+			const bool inside = row >= row0 && row < row0 + 32 && row < m && col >= col0 && col < col0 + 32 && col < n;
+			const float got = c[(size_t)row * ldc + col];
+			if (inside ? got != value(row, col) : got == got) { good = false; break; }
+		}
+	std::printf("epilogue store m=%d n=%d block at (%d, %d): %s\n", m, n, row0, col0, good ? "ok" : "FAIL");
+	return good;
+}
+
 // one gravity step: both kernels (scalar loop; packed f32x2 loop with its padded tail tile) against a float64 evaluation of the same formula
 static bool check_nbody(int n, bool packed) {
 	auto x = random_matrix((size_t)n * 3, (unsigned)n);
@@ -153,6 +189,13 @@ int main() {
 	ok &= check_nbody(1500, false);
 	ok &= check_nbody(4096, true);
 	ok &= check_nbody(5000, true);
+	// the tcgen05 matmul's epilogue store (octet transpose by shuffles): full block, ragged rows, ragged columns (float4 and scalar tails),
+	// a block entirely outside, N smaller than a block
+	ok &= check_epilogue_store(64, 128, 32, 96);
+	ok &= check_epilogue_store(50, 128, 32, 0);
+	ok &= check_epilogue_store(64, 44, 0, 32);
+	ok &= check_epilogue_store(70, 12, 64, 0);
+	ok &= check_epilogue_store(20, 64, 32, 32);
 	// control: the hardware-validated weight-gradient kernel through the same harness
 	ok &= check_tn<64, 128, 8, 8>(1000, 48, 128, 5);
 	ok &= check_tn<64, 128, 8, 8>(500, 100, 200, 3);   // several tiles in both directions, ragged in both (grouped column layout of the 8-wide tile)
