@@ -2,7 +2,7 @@
 thread (size threshold lowered so that the 256 x 256 program takes the lane code, edge paths included at 100 x 72) against the same
 program emitted with one element per thread, in two processes.  The lane code is the same statements replicated per lane, so the
 fields agree to rounding (a product shared by two lanes may be contracted into an FMA in one form and not in the other: the bar is
-1e-5 of each field's maximum, a tenth of the parity bar against the reference); the CPU suite checks bit-identity on the host
+5e-5 of each field's maximum, half of the loosest parity bar against the reference); the CPU suite checks bit-identity on the host
 (tests/test_coarsening_cpu.py)."""
 import json
 import os
@@ -64,4 +64,4 @@ def test_lane_code_matches_one_element_per_thread_on_the_device(tmp_path):
         a, b = plain[k].astype(np.float64), lanes[k].astype(np.float64)
         assert a.shape == b.shape, k
         scale = max(np.abs(a).max(), 1e-30)
-        assert np.isfinite(b).all() and np.abs(a - b).max() <= 1e-5 * scale, (k, float(np.abs(a - b).max()), float(scale))
+        assert np.isfinite(b).all() and np.abs(a - b).max() <= 5e-5 * scale, (k, float(np.abs(a - b).max()), float(scale))
