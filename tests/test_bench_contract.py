@@ -68,8 +68,9 @@ def test_cuda_arm_line_has_every_contract_key(monkeypatch):
     e2e = line["e2e"]
     assert e2e["h2d_bytes_per_step"] == 4 * 2048 * 2048 * 4 == e2e["d2h_bytes_per_step"] and e2e["unit"] == "GB/s"
     # every step uploads its 4 input fields and downloads its 4 result fields inside the timed region (copy streams); the same loop
-    # runs max(warmup, 3) untimed steps first
-    total = args.steps + max(args.warmup, 3)
+    # runs the reported number of untimed steps first (at least bench.FLUID_WARMUP: graph instantiation must lie outside the timed region)
+    total = args.steps + bench.fluid_warmup(args)
+    assert line["warmup"] == bench.fluid_warmup(args) >= 8
     assert dev.uploads == 4 * total and dev.downloads == 4 * total and dev.waits == total and dev.copy_syncs == 2
     assert line["config"] == bench.fluid_config(2048)  # identical to the reference arm's (the driver compares the two arms' configs)
     assert bench.fluid_step_bytes(2048) == 816840772  # = the live count of the runtime profiler on the B200 (BENCH_r01.json)
