@@ -477,7 +477,9 @@ void GenerateCUDAKernel(Program* program, Kernel* kernel) {
 			const CudaCoarsening c = it->second;
 			if (c.dim < 3 && c.factor > 1 && group[c.dim] % c.factor == 0) {
 				const int real_extent = group[c.dim] / c.factor;
-				string lanes = CoarsenBody(body, c, real_extent);
+				// TFCUDA_COARSEN_FORCE_LOOP=1 (test aid): skip the replication so that the lane-loop fallback is exercised
+				static const bool force_loop = getenv("TFCUDA_COARSEN_FORCE_LOOP") && atoi(getenv("TFCUDA_COARSEN_FORCE_LOOP")) != 0;
+				string lanes = force_loop ? string() : CoarsenBody(body, c, real_extent);
 				if (lanes.empty()) lanes = LaneLoopBody(body, c, real_extent);
 				if (!lanes.empty()) {
 					body = lanes;

@@ -295,6 +295,7 @@ def main():
                 seen += len(kernels)
                 lib = build(fluid.compiled_code(), kernels, "fluid")
                 result[f"{spec}/coarsened"] = coarsened(kernels)
+                result[f"{spec}/lane_loops"] = np.array(sum("tf_lane" in k[0][2] and "lanes per thread" not in k[0][2] for k in kernels))
 
                 def call(*state):
                     arrays = [t.numpy if isinstance(t, HostTensor) else t for t in state]

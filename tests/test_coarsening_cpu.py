@@ -39,7 +39,9 @@ def test_lane_code_is_bit_identical_to_one_element_per_thread(tmp_path):
     _ready()
     runs = {"off": _sim(tmp_path, "off", {"TFCUDA_COARSEN": "0"}, SPECS),
             "x4": _sim(tmp_path, "x4", {"TFCUDA_COARSEN_MIN_ELEMENTS": "1"}, SPECS),
-            "x2": _sim(tmp_path, "x2", {"TFCUDA_COARSEN_MIN_ELEMENTS": "1", "TFCUDA_COARSEN": "2"}, SPECS)}
+            "x2": _sim(tmp_path, "x2", {"TFCUDA_COARSEN_MIN_ELEMENTS": "1", "TFCUDA_COARSEN": "2"}, SPECS),
+            # the fallback for bodies the replication does not accept: the lanes one after the other around the untouched text
+            "loop": _sim(tmp_path, "loop", {"TFCUDA_COARSEN_MIN_ELEMENTS": "1", "TFCUDA_COARSEN_FORCE_LOOP": "1"}, SPECS)}
     got = {}
     for tag, (out, proc) in runs.items():
         _, err = proc.communicate(timeout=1200)
@@ -48,10 +50,12 @@ def test_lane_code_is_bit_identical_to_one_element_per_thread(tmp_path):
             got[tag] = {k: z[k] for k in z.files}
     for spec in SPECS:
         assert got["off"][f"{spec}/coarsened"][0] == 0
-        for tag in ("x4", "x2"):
+        assert got["loop"][f"{spec}/lane_loops"] >= 5 and got["loop"][f"{spec}/coarsened"][0] == 0, spec
+        for tag in ("x4", "x2", "loop"):
             lanes, with_edge_path, kernels = got[tag][f"{spec}/coarsened"]
-            assert lanes >= 5, (spec, tag, lanes, kernels)  # the full-resolution stencils at least (coarser multigrid levels may be too short)
-            assert (with_edge_path > 0) == (spec != "fluid:64:96:3"), (spec, tag, with_edge_path)
+            if tag != "loop":
+                assert lanes >= 5, (spec, tag, lanes, kernels)  # the full-resolution stencils at least (coarser multigrid levels may be too short)
+                assert (with_edge_path > 0) == (spec != "fluid:64:96:3"), (spec, tag, with_edge_path)
             for k in range(6):  # vx, vy, pressure, density, div, canvas
                 a, b = got[tag][f"{spec}/{k}"], got["off"][f"{spec}/{k}"]
                 assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32)), (spec, tag, k)
