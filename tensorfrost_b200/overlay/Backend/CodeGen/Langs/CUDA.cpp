@@ -167,14 +167,16 @@ vector<int> CudaDefaultGroupSize(int dims, const vector<int>& const_shape, Node*
 	const int factor = CudaCoarsenFactor();
 	if (group.empty() || factor <= 1 || kernel_node == nullptr) return group;
 	// large, constant shape only: the grid must still fill the machine after losing `factor` of its blocks (148 SMs x 8 blocks of 256
-	// threads = 1184 blocks per wave), and a short kernel is launch-bound, not bandwidth-bound
+	// threads = 1184 blocks per wave), and a short kernel is launch-bound, not bandwidth-bound.  The bar is 2^20 elements: 1024 blocks
+	// of 256 threads, one full wave (measured at 2^22: the fluid stencil kernels -25 .. -41 %; the 1024^2 multigrid level is the same code
+	// at 2^20, where the issue time of one wave halves; at 2^18 the grid would leave SMs idle)
 	long long elements = 1;
 	for (int i = 0; i < dims; i++) {
 		if (i >= (int)const_shape.size() || const_shape[i] <= 0) return group;
 		elements *= const_shape[i];
 	}
 	// TFCUDA_COARSEN_MIN_ELEMENTS: the threshold, so that the host-execution tests can run their small cases through the lane code
-	static const long long min_elements = getenv("TFCUDA_COARSEN_MIN_ELEMENTS") ? atoll(getenv("TFCUDA_COARSEN_MIN_ELEMENTS")) : (1ll << 22);
+	static const long long min_elements = getenv("TFCUDA_COARSEN_MIN_ELEMENTS") ? atoll(getenv("TFCUDA_COARSEN_MIN_ELEMENTS")) : (1ll << 20);
 	if (elements < min_elements) return group;
 	int threads = 1;
 	for (int g : group) threads *= g;

@@ -62,9 +62,9 @@ def test_lane_code_is_bit_identical_to_one_element_per_thread(tmp_path):
 
 
 def test_which_kernels_of_the_benchmark_programs_get_lanes(tmp_path):
-    """At the benchmark size (2048 x 2048) the five full-resolution stencil kernels of the fluid step are coarsened, the multigrid
-    sweeps on the 512 / 1024 grids (launch-bound, too few blocks) and the two long kernels (advection: 84 data-dependent gathers; final
-    projection: no gain measured) are not; the
+    """At the benchmark size (2048 x 2048) the ten stencil kernels of the 2048 and 1024 grids are coarsened; the kernels of the 512
+    grid (too few blocks left to fill the machine) and the two long kernels (advection: 84 data-dependent gathers; final projection:
+    no gain measured) are not; the
     kernel text states the block it must be launched with, which differs from the block of the host program's dispatch."""
     _ready()
     script = r"""
@@ -93,7 +93,7 @@ print("NVRTC", rc, abi.lib().tfcuda_last_error().decode(errors="replace")[:2000]
     rows = [l.split() for l in r.stdout.splitlines() if l.startswith("KERNEL")]
     assert len(rows) == 15
     lanes = [row for row in rows if row[2] == "1"]
-    assert len(lanes) == 5, rows
+    assert len(lanes) == 10, rows
     for _, kid, _, block, ir_block, _ in lanes:
         assert block == "32,8,1" and ir_block == "32,32", (kid, block, ir_block)
     for _, kid, flag, block, ir_block, n_lines in rows:

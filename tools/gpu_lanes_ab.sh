@@ -18,8 +18,8 @@ except Exception as e:
     print(sys.argv[1], "no line:", e)
 PY
 }
-# fluid 2048^2: default, no lanes, no range fact either (= the build measured in DESIGN.md 6), 2 lanes, lanes from 2^20 elements on
-for tag in default:"" nolanes:"TFCUDA_COARSEN=0" measured:"TFCUDA_COARSEN=0 TFCUDA_ASSUME=0" lanes2:"TFCUDA_COARSEN=2" from1m:"TFCUDA_COARSEN_MIN_ELEMENTS=1048576"; do
+# fluid 2048^2: default, no lanes, no range fact either (= the build measured in DESIGN.md 6), 2 lanes, lanes from 2^22 elements on only
+for tag in default:"" nolanes:"TFCUDA_COARSEN=0" measured:"TFCUDA_COARSEN=0 TFCUDA_ASSUME=0" lanes2:"TFCUDA_COARSEN=2" from4m:"TFCUDA_COARSEN_MIN_ELEMENTS=4194304"; do
   name=${tag%%:*}; envs=${tag#*:}
   env $envs timeout -k 10 120 python bench.py --no-extra --no-cpu --no-nca --no-verify > "$OUT/fluid_$name.log" 2> "$OUT/fluid_$name.err"; summ "$OUT/fluid_$name.log"
 done
